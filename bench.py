@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — spin-steps/s of the `sim` hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4]
+
+A "step" is one pass of the hot path over the whole workload: all spins x all scales x all
+timepoints of one phantom (what one iteration of the reference's phantom loop does,
+src/sim/monte_carlo.cu:227-349).  Default workload = BASELINE.json configs[1]: SE BOLD (config/se.ini),
+600^3 cylinder vessel phantom with susceptibility field map, 1e7 spins, the 50 FoV scales of
+config/config_default.ini => 4.0e11 spin-steps per pass.
+
+  value  whole-job throughput, inputs resident in HBM, device time (CUDA events on the engine's stream,
+         max over ranks), output zero-fill included.
+  e2e    same metric through swk_run(): HOST buffers in (pinned XYZ0), HOST buffers out (pinned M1, XYZ1, T
+         + sums), H2D and D2H inside the timed region.
+Under torchrun (N > 1) every rank simulates its own shard of N x spins (weak scaling), the phantom is
+replicated, and the per-echo ensemble sums are all-reduced with NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_SCALES = [0.0125, 0.0147, 0.0173, 0.0204, 0.0240, 0.0283, 0.0333, 0.0392, 0.0462, 0.0544, 0.0641, 0.0754, 0.0888,
+                  0.1046, 0.1231, 0.1450, 0.1707, 0.2010, 0.2367, 0.2787, 0.3282, 0.3865, 0.4551, 0.5358, 0.6309, 0.7429,
+                  0.8748, 1.0301, 1.2129, 1.4282, 1.6817, 1.9803, 2.3318, 2.7456, 3.2330, 3.8069, 4.4826, 5.2783, 6.2152,
+                  7.3184, 8.6174, 10.1470, 11.9481, 14.0689, 16.5662, 19.5067, 22.9692, 27.0463, 31.8471, 37.5000]  # config_default.ini:78-127
+
+
+def workload(name: str, n_spins: int | None, n_scales: int | None):
+    """Returns (SimConfig kwargs, phantom spec, description).  INI values of config/*.ini + config_default.ini."""
+    base = dict(timestep_us=50, B0=9.4, seed=10, cross_fov=0, max_iterations=10000, diffusivity=[1e-9, 1e-9],
+                T1_ms=[2200.0, 2200.0], T2_ms=[41.0, 41.0], pXY=[1.0, 0.0, 0.0, 1.0], scales=list(DEFAULT_SCALES), scale_type=0)
+    if name == "c2":
+        cfg = dict(base, TR_us=40000, TE_us=[20000], RF_FA_deg=[90.0, 180.0], RF_PH_deg=[0.0, 90.0], RF_T_us=[0, 10000])
+        ph = dict(kind="cylinder", n=600, fov_um=600.0, radius_um=8.0, bvf=4.0, Y=0.78, seed=0)
+        S, desc = 10_000_000, "C2 SE BOLD (config/se.ini), 600^3 cylinder phantom r=8um BVF 4% + fieldmap, 1e7 spins, 50 FoV scales"
+    elif name == "c1":
+        cfg = dict(base, TR_us=40000, TE_us=[20000], RF_FA_deg=[90.0], RF_PH_deg=[0.0], RF_T_us=[0])
+        ph = dict(kind="cylinder", n=100, fov_um=100.0, radius_um=8.0, bvf=4.0, Y=0.78, seed=0)
+        S, desc = 100_000, "C1 GRE BOLD (config/gre.ini), 100^3 cylinder phantom, 1e5 spins, 50 FoV scales"
+    elif name == "c4":
+        cfg = dict(base, TR_us=10000, TE_us=[5000], RF_FA_deg=[16.0], RF_PH_deg=[0.0], RF_T_us=[0], n_dummy_scan=-1,
+                   linear_phase_cycling=180.0, scales=[1.0])
+        ph = dict(kind="cylinder", n=600, fov_um=600.0, radius_um=8.0, bvf=4.0, Y=0.78, seed=0)
+        S, desc = 10_000_000, "C4 bSSFP (config/ssfp.ini), 1101 TRs x 200 steps, 600^3 cylinder phantom, 1e7 spins, 1 scale"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    if n_spins:
+        S = n_spins
+    if n_scales:
+        cfg["scales"] = cfg["scales"][:: max(1, len(cfg["scales"]) // n_scales)][:n_scales]
+    cfg["n_spins"] = S
+    return cfg, ph, desc
+
+
+def make_phantom_2d(ph):
+    from spinwalk_b200.phantoms import cylinder_phantom
+
+    return cylinder_phantom(ph["n"], ph["fov_um"], radius_um=ph["radius_um"], bvf_pct=ph["bvf"], Y=ph["Y"], seed=ph["seed"], planar=True)
+
+
+def make_positions(S, fov, seed, first=0):
+    """uniform in [1%,99%] of the FoV (distribution of monte_carlo.cu:142-151); numpy stream, chunked by global id."""
+    rng = np.random.default_rng([seed, first])
+    x = rng.random((S, 3), dtype=np.float32)
+    f = np.asarray(fov, np.float32)
+    return x * (np.float32(0.98) * f) + np.float32(0.01) * f
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0, threads=None):
+    """The reference's own CPU implementation of the path (oracle/_ref/libswref_cpu.so = unmodified kernels.cu built
+    by g++, std::mt19937 arithmetic; falls back to the C port) on a bounded sample of the same workload."""
+    from oracle import pyoracle as po
+
+    n, nz = ph["n"], ph["n"]
+    mask = np.ascontiguousarray(np.broadcast_to(mask2[:, :, None], (n, n, nz)))
+    fm = np.ascontiguousarray(np.broadcast_to(fm2[:, :, None], (n, n, nz)))
+    threads = threads or os.cpu_count() or 1
+    kind = "reference" if po.have_ref_cpu() else "port"
+    if kind == "port":
+        po.build(ref=False)
+
+    def run(n_spins, scales):
+        c = po.Case(fov=tuple(fov), phantom_size=(n, n, nz), n_spins=n_spins, TR_us=cfg_kw["TR_us"], timestep_us=cfg_kw["timestep_us"],
+                    seed=cfg_kw["seed"], B0=cfg_kw["B0"], TE_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["TE_us"]],
+                    RF_FA_deg=cfg_kw["RF_FA_deg"], RF_PH_deg=cfg_kw["RF_PH_deg"], RF_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["RF_T_us"]],
+                    n_dummy_scan=cfg_kw.get("n_dummy_scan", 0), linear_phase_cycling=cfg_kw.get("linear_phase_cycling", 0.0),
+                    diffusivity=cfg_kw["diffusivity"], T1_ms=cfg_kw["T1_ms"], T2_ms=cfg_kw["T2_ms"], pXY=cfg_kw["pXY"],
+                    scales=scales, scale_type=cfg_kw["scale_type"], cross_fov=cfg_kw["cross_fov"], max_iterations=cfg_kw["max_iterations"])
+        x0 = make_positions(n_spins, fov, cfg_kw["seed"])
+        f = po.run_ref if kind == "reference" else po.run_oracle
+        r = f(c, fm, mask, x0, flavour=po.RNG_MT19937, threads=threads)
+        return c.total_steps(), r["seconds"]
+
+    scales = cfg_kw["scales"]
+    steps, sec = run(max(threads * 8, 256), scales[:: max(1, len(scales) // 5)][:5])  # calibration
+    rate = steps / max(sec, 1e-6)
+    per_spin = len(scales) * (steps / (max(threads * 8, 256) * min(5, len(scales))))
+    n_spins = int(max(threads * 8, min(cfg_kw["n_spins"], rate * target_s / per_spin)))
+    steps, sec = run(n_spins, scales)
+    return {"value": steps / sec, "unit": "spin-steps/s", "cores": threads, "kind": kind,
+            "sample": f"first {n_spins} spins x all {len(scales)} scales of the workload ({steps:.3g} spin-steps, {sec:.1f} s); "
+                      f"low spin ids keep mt19937::discard(seed+spin) cheap, which flatters the CPU reference (SURVEY App. B-3)"}, steps, sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--spins", type=int, default=0, help="override spins per GPU (debug; makes the number non-headline)")
+    ap.add_argument("--scales", type=int, default=0, help="override number of scales (debug)")
+    ap.add_argument("--mode", default="fast", choices=["fast", "compat"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    cfg_kw, ph, desc = workload(args.workload, args.spins or None, args.scales or None)
+    S_per_gpu = cfg_kw["n_spins"]
+    K = len(cfg_kw["scales"])
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        mask2, fm2, fov = make_phantom_2d(ph)
+        vals, samples = [], None
+        tgt = 12.0
+        for i in range(args.warmup + args.steps):
+            cb, steps, sec = cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=tgt if i >= args.warmup else 3.0)
+            if i >= args.warmup:
+                vals.append((steps, sec))
+                samples = cb
+        tot_steps = sum(v[0] for v in vals)
+        tot_sec = sum(v[1] for v in vals)
+        v = tot_steps / tot_sec
+        samples["value"] = v
+        print(json.dumps({"impl": "reference", "metric": "spin-steps/s", "value": v, "unit": "spin-steps/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / max(1, args.steps),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+                          "data": "synthetic", "config": {"workload": desc, "note": "each step = bounded sample of the workload on host cores"},
+                          "cpu_baseline": samples, "gpu_launches": 0,
+                          "e2e": {"value": v, "unit": "spin-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+
+    import spinwalk_b200 as sw
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    mode = sw.MODE_FAST if args.mode == "fast" else sw.MODE_COMPAT
+    cfg_kw_global = dict(cfg_kw, n_spins=S_per_gpu * world)  # weak scaling: global population grows with N
+    cfg = sw.SimConfig(**cfg_kw_global)
+    mask2, fm2, fov = make_phantom_2d(ph)
+    n = ph["n"]
+    mask_d = torch.from_numpy(mask2).to(dev)[:, :, None].expand(n, n, n).contiguous()
+    fm_d = torch.from_numpy(fm2).to(dev)[:, :, None].expand(n, n, n).contiguous()
+
+    spin_first = rank * S_per_gpu
+    xyz0_pin = torch.empty((S_per_gpu, 3), dtype=torch.float32, pin_memory=True)
+    xyz0_pin.numpy()[:] = make_positions(S_per_gpu, fov, cfg.seed, spin_first)
+
+    eng = sw.Engine(local_rank)
+    eng.set_phantom(mask_d, fm_d, fov)
+    del mask_d, fm_d
+    eng.set_sequence(cfg)
+    eng.set_spins(xyz0_pin.numpy(), None, spin_first)
+    E, ns = cfg.n_TE, cfg.n_substrate
+    sums_d = torch.zeros((K, E, ns, 4), dtype=torch.float64, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_pass():
+        st = eng.run_device(mode=mode, flags=sw.OUT_ALL, d_sums_ptr=sums_d.data_ptr())
+        if world > 1:  # the one collective of the path: a few KB of per-echo ensemble sums
+            dist.all_reduce(sums_d, op=dist.ReduceOp.SUM)
+        return st
+
+    # counters (voxel changes etc.) for the roofline's algorithmic bytes: same inputs, STATS kernel variant, untimed
+    st_counts = eng.run_device(mode=mode, flags=sw.OUT_ALL | sw.RUN_STATS, d_sums_ptr=sums_d.data_ptr())
+
+    for _ in range(args.warmup):
+        one_pass()
+    barrier()
+    dev_ms, ker_ms = 0.0, 0.0
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st = one_pass()
+            dev_ms += st["device_ms"]
+            ker_ms += st["kernel_ms"]
+        barrier()
+        wall_s = time.perf_counter() - t0
+    clocks = clk.summary()
+    t = torch.tensor([dev_ms, ker_ms, wall_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, ker_ms, wall_ms = (float(v) for v in t.tolist())
+    steps_per_pass_rank = S_per_gpu * K * (eng.n_dummy_scan + 1) * cfg.n_timepoints
+    total_steps = steps_per_pass_rank * world * args.steps
+    value = total_steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end through swk_run with host buffers
+    e2e = None
+    if not args.no_e2e:
+        out = (torch.empty((K, S_per_gpu, E, 3), dtype=torch.float32, pin_memory=True),
+               torch.empty((K, S_per_gpu, eng.trj, 3), dtype=torch.float32, pin_memory=True),
+               torch.empty((K, S_per_gpu, E), dtype=torch.uint8, pin_memory=True))
+        out_np = tuple(o.numpy() for o in out)
+        h2d = xyz0_pin.numel() * 4 + K * 4
+        d2h = sum(o.numel() * o.element_size() for o in out) + K * E * ns * 4 * 8
+        eng.run(xyz0_pin.numpy(), None, spin_first, mode=mode, out=out_np, stats=False)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = eng.run(xyz0_pin.numpy(), None, spin_first, mode=mode, out=out_np, stats=False)
+            if world > 1:
+                sums_d.copy_(torch.from_numpy(r["sums"]))
+                dist.all_reduce(sums_d, op=dist.ReduceOp.SUM)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_steps / float(te.item()), "unit": "spin-steps/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * float(te.item()) / args.steps,
+               "api": "swk_run (C-ABI) with pinned host buffers: XYZ0 in; M1, XYZ1, T, sums out"}
+        del out, out_np
+
+    # ---- roofline of the walk kernel: algorithmic bytes / mean launch duration
+    peak, peak_src = measured_peaks()
+    per_pass_bytes = (st_counts["mask_gathers"] * 1 + st_counts["field_gathers"] * 4
+                      + S_per_gpu * K * (24 + 13 * E + 12))
+    ker_ms_per_launch = ker_ms / args.steps
+    achieved = per_pass_bytes / (ker_ms_per_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "swk::walk_kernel<FAST>" if mode == sw.MODE_FAST else "swk::walk_kernel<COMPAT>",
+                "algorithmic_bytes_per_launch": per_pass_bytes, "kernel_ms_per_launch": ker_ms_per_launch,
+                "bytes_per_spin_step": per_pass_bytes / steps_per_pass_rank,
+                "p_voxel_change": st_counts["mask_gathers"] / max(1, st_counts["steps"]),
+                "rejects_per_step": st_counts["rejects"] / max(1, st_counts["steps"]),
+                "note": "gather-latency/issue-bound kernel: algorithmic bytes are ~1-5 B per spin-step, so the HBM fraction is "
+                        "small by construction; see profiles/ for issue-slot and L2 sector counters"}
+
+    line = {"metric": "spin-steps/s", "value": value, "unit": "spin-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if mode == sw.MODE_FAST else "f32+f64", "data": "synthetic",
+            "config": {"workload": desc, "spins_per_gpu": S_per_gpu, "n_scales": K, "timepoints": cfg.n_timepoints,
+                       "scans": eng.n_dummy_scan + 1, "spin_steps_per_pass": steps_per_pass_rank * world,
+                       "rng": "philox4x32-10 + Box-Muller (SWK_MODE_FAST)" if mode == sw.MODE_FAST else "minstd_rand + erfcinvf (SWK_MODE_COMPAT, reference arithmetic)",
+                       "l2": "inputs larger than L2 (phantom 1.08 GB vs 126 MB)" if ph["n"] >= 400 else "phantom fits in L2; outputs (>L2) rewritten every pass",
+                       "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums"},
+            "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": args.steps * st["n_launches"],
+            "e2e": e2e, "roofline": roofline, "lost_spins": st_counts["lost"]}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cb, _, _ = cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0)
+            line["cpu_baseline"] = cb
+        except Exception as ex:  # the baseline is a reported extra; never lose the GPU line over it
+            line["cpu_baseline"] = {"value": None, "unit": "spin-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,48 @@
+"""Build the CUDA engine in-tree: spinwalk_b200/libspinwalk_b200.so (sm_100a only, no other arch, no fallback)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", "engine.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", "walk_kernel.cuh"), os.path.join(HERE, "..", "include", "spinwalk_engine.h")]
+OUT = os.path.join(HERE, "libspinwalk_b200.so")
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def stale() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return OUT
+    cmd = [nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT, *SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libspinwalk_b200.so")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

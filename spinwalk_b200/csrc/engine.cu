@@ -1,0 +1,551 @@
+// spinwalk_b200/csrc/engine.cu — C-ABI (include/spinwalk_engine.h) over the sm_100a walk kernel.
+//
+// Host-side counterpart of the device branch of sim::monte_carlo::run (src/sim/monte_carlo.cu:247-337)
+// and of save()'s D2H copies (:170-176): owns device memory, validates and stages the sequence,
+// launches ONE kernel for all scales, and hands results back in the reference's layouts.
+// No CPU fallback exists: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "walk_kernel.cuh"
+
+using namespace swk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+} // namespace
+
+struct swk_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evA = nullptr, ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+
+    // phantom
+    DevBuf mask, fieldmap;
+    uint64_t dims[3] = {0, 0, 0};
+    float fov[3] = {0, 0, 0};
+    uint32_t mask_substrates = 0;
+    bool has_phantom = false;
+
+    // sequence
+    swk_params P{};
+    BlobLayout L{};
+    std::vector<uint8_t> blob_h;
+    DevBuf blob;
+    float rf_ph0 = 0.f;
+    bool has_sequence = false;
+
+    // spins
+    DevBuf xyz0, m0;
+    uint32_t spin_first = 0, n_local = 0;
+    bool has_m0 = false, has_spins = false;
+
+    // run state / outputs
+    DevBuf scales, M1, XYZ1, T, sums, counters;
+    uint32_t n_scales = 0, n_te = 0;
+    uint64_t trj = 1;
+    int out_flags = 0;
+    double *last_sums = nullptr; // device pointer actually used by the last run
+    swk_stats stats{};
+};
+
+namespace {
+
+int fail(swk_engine *e, int code, const std::string &msg)
+{
+    if (e) e->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(e, SWK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+void release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+// (re)allocate exactly `bytes` (0 => free)
+int ensure(swk_engine *e, DevBuf &b, size_t bytes)
+{
+    if (b.bytes == bytes && (b.p || bytes == 0)) return SWK_OK;
+    release(b);
+    if (bytes == 0) return SWK_OK;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes > free_b) { // ≙ check_memory_size (device_helper.cu:78-101)
+        char msg[160];
+        snprintf(msg, sizeof msg, "not enough device memory: need %.1f MB, free %.1f MB", bytes / 1048576.0, free_b / 1048576.0);
+        return fail(e, SWK_ERR_MEMORY, msg);
+    }
+    CK(cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return SWK_OK;
+}
+
+__global__ void mask_max_kernel(const uint8_t *mask, size_t n, unsigned int *out)
+{
+    unsigned int m = 0;
+    const size_t n16 = n / 16;
+    const uint4 *v = reinterpret_cast<const uint4 *>(mask);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 w = __ldg(v + i);
+        unsigned int a = __vmaxu4(__vmaxu4(w.x, w.y), __vmaxu4(w.z, w.w));
+        a = max(max(a & 0xffu, (a >> 8) & 0xffu), max((a >> 16) & 0xffu, a >> 24));
+        m = max(m, a);
+    }
+    for (size_t i = n16 * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = max(m, (unsigned int)mask[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+bool ascending(const int32_t *t, uint32_t n)
+{
+    for (uint32_t i = 1; i < n; i++)
+        if (t[i] <= t[i - 1]) return false;
+    return true;
+}
+
+uint32_t put(std::vector<uint8_t> &b, const void *src, size_t bytes)
+{
+    while (b.size() % 8) b.push_back(0);
+    uint32_t off = (uint32_t)b.size();
+    const uint8_t *s = static_cast<const uint8_t *>(src);
+    b.insert(b.end(), s, s + bytes);
+    return off;
+}
+
+} // namespace
+
+extern "C" {
+
+int swk_version(void) { return SWK_VERSION_MAJOR * 100 + SWK_VERSION_MINOR; }
+
+int swk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *swk_last_error(const swk_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int swk_create(int device_id, swk_engine **out)
+{
+    swk_engine *e = nullptr;
+    if (!out) return fail(nullptr, SWK_ERR_INVALID, "swk_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n <= 0)
+        return fail(nullptr, SWK_ERR_CUDA, std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0") +
+                                               " (this engine has no CPU fallback)");
+    if (device_id < 0 || device_id >= n) {
+        char msg[128];
+        snprintf(msg, sizeof msg, "device id %d is not available; number of GPUs is %d", device_id, n);
+        return fail(nullptr, SWK_ERR_INVALID, msg);
+    }
+    e = new swk_engine();
+    e->device = device_id;
+    cudaDeviceProp prop{};
+    if ((ce = cudaSetDevice(device_id)) != cudaSuccess || (ce = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess ||
+        (ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaEventCreate(&e->evA)) != cudaSuccess || (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess) {
+        std::string m = std::string("swk_create: ") + cudaGetErrorString(ce);
+        delete e;
+        return fail(nullptr, SWK_ERR_CUDA, m);
+    }
+    e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = e;
+    return SWK_OK;
+}
+
+void swk_destroy(swk_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (DevBuf *b : {&e->mask, &e->fieldmap, &e->blob, &e->xyz0, &e->m0, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters})
+        release(*b);
+    if (e->evA) cudaEventDestroy(e->evA);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int swk_prepare(swk_params *p, float RF_FA0_deg, float T1_0_ms, const double *diffusivity_m2s, uint32_t n, double *sigma_out)
+{
+    if (!p || p->timestep_us <= 0) return SWK_ERR_INVALID;
+    p->c = cosf(RF_FA0_deg * kDeg2Rad); // simulation_parameters.cuh:229-230
+    p->s = sinf(RF_FA0_deg * kDeg2Rad);
+    p->n_timepoints = (uint32_t)(p->TR_us / p->timestep_us);
+    for (uint32_t i = 0; i < n && diffusivity_m2s && sigma_out; i++)
+        sigma_out[i] = 1e-3 * sqrt(2. * diffusivity_m2s[i] * p->timestep_us); // :236-237
+    if (p->n_dummy_scan < 0) p->n_dummy_scan = 5.0 * T1_0_ms / float(p->TR_us * 1e-3); // :239-242
+    return SWK_OK;
+}
+
+int swk_set_phantom(swk_engine *e, const uint8_t *mask, const float *fieldmap_T, const uint64_t dims[3], const float fov_m[3], int on_device)
+{
+    if (!e) return SWK_ERR_INVALID;
+    if (!mask || !dims || !fov_m) return fail(e, SWK_ERR_INVALID, "swk_set_phantom: mask, dims and fov are mandatory");
+    for (int i = 0; i < 3; i++)
+        if (dims[i] == 0 || dims[i] > 0x7fffffffull || !(fov_m[i] > 0.f)) return fail(e, SWK_ERR_INVALID, "swk_set_phantom: bad dims or fov");
+    CK(cudaSetDevice(e->device));
+    const size_t V = (size_t)dims[0] * dims[1] * dims[2];
+    e->has_phantom = false;
+    release(e->mask); // ≙ cleanup_device (monte_carlo.cu:86-95)
+    release(e->fieldmap);
+    int rc;
+    if ((rc = ensure(e, e->mask, V)) != SWK_OK) return rc;
+    if (fieldmap_T && (rc = ensure(e, e->fieldmap, V * sizeof(float))) != SWK_OK) return rc;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CK(cudaMemcpyAsync(e->mask.p, mask, V, kind, e->stream));
+    if (fieldmap_T) CK(cudaMemcpyAsync(e->fieldmap.p, fieldmap_T, V * sizeof(float), kind, e->stream));
+    // number of substrates present = max(mask)+1 (monte_carlo.cu:113)
+    if ((rc = ensure(e, e->counters, 8 * sizeof(unsigned long long))) != SWK_OK) return rc;
+    CK(cudaMemsetAsync(e->counters.p, 0, e->counters.bytes, e->stream));
+    mask_max_kernel<<<e->sm_count * 8, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), V, static_cast<unsigned int *>(e->counters.p));
+    CK(cudaGetLastError());
+    unsigned int mx = 0;
+    CK(cudaMemcpyAsync(&mx, e->counters.p, sizeof mx, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->mask_substrates = mx + 1;
+    for (int i = 0; i < 3; i++) { e->dims[i] = dims[i]; e->fov[i] = fov_m[i]; }
+    e->has_phantom = true;
+    return SWK_OK;
+}
+
+int swk_set_sequence(swk_engine *e, const swk_params *p, const swk_tables *t)
+{
+    if (!e) return SWK_ERR_INVALID;
+    if (!p || !t) return fail(e, SWK_ERR_INVALID, "swk_set_sequence: NULL argument");
+    // ---- validation ≙ config_reader::check (config_reader.cpp:195-324) ----
+    const uint32_t ns = p->n_substrate;
+    if (ns < 1 || ns > 255) return fail(e, SWK_ERR_INVALID, "at least one (and at most 255) substrates are required");
+    if (t->n_step_sigma != ns || t->n_T1 != ns || t->n_T2 != ns || t->n_pXY != ns * ns || !t->step_sigma_m || !t->T1_ms || !t->T2_ms || !t->pXY)
+        return fail(e, SWK_ERR_INVALID, "DIFFUSIVITY, T1, T2 must have n_substrate entries and P_XY n_substrate^2");
+    if (t->n_RF < 1 || t->n_RF_FA != t->n_RF || t->n_RF_PH != t->n_RF || !t->RF_tp || !t->RF_FA_deg || !t->RF_PH_deg)
+        return fail(e, SWK_ERR_INVALID, "RF_FA, RF_PH and RF_T must have the same number of elements (>= 1)");
+    if (t->RF_tp[0] != 0) return fail(e, SWK_ERR_INVALID, "the first RF start time must be 0");
+    if (t->n_dephasing_deg != t->n_dephasing) return fail(e, SWK_ERR_INVALID, "DEPHASING and DEPHASING_T must have the same number of elements");
+    if (t->n_gradX != t->n_gradient || t->n_gradY != t->n_gradient || t->n_gradZ != t->n_gradient)
+        return fail(e, SWK_ERR_INVALID, "GRADIENT_X/Y/Z and GRADIENT_T must have the same number of elements");
+    if (t->n_RF > 65535 || t->n_TE > 65535 || t->n_dephasing > 65535 || t->n_gradient > 65535)
+        return fail(e, SWK_ERR_INVALID, "event tables are limited to 65535 entries (uint16 counters, kernels.cu:125)");
+    if (!ascending(t->RF_tp, t->n_RF) || !ascending(t->TE_tp, t->n_TE) || !ascending(t->dephasing_tp, t->n_dephasing) ||
+        !ascending(t->gradient_tp, t->n_gradient))
+        return fail(e, SWK_ERR_INVALID, "RF_T, TE, DEPHASING_T and GRADIENT_T must be sorted in strictly ascending order");
+    for (uint32_t i = 0; i < t->n_TE; i++)
+        if (t->TE_tp[i] < 0) return fail(e, SWK_ERR_INVALID, "TE must be >= 0");
+    for (uint32_t i = 0; i < t->n_dephasing; i++)
+        if (t->dephasing_tp[i] < 0) return fail(e, SWK_ERR_INVALID, "DEPHASING_T must be >= 0");
+    for (uint32_t i = 0; i < t->n_gradient; i++)
+        if (t->gradient_tp[i] < 0) return fail(e, SWK_ERR_INVALID, "GRADIENT_T must be >= 0");
+    if (p->timestep_us <= 0 || p->TR_us <= 0 || p->n_timepoints == 0) return fail(e, SWK_ERR_INVALID, "TR and TIME_STEP must be positive");
+    if (p->n_dummy_scan < 0) return fail(e, SWK_ERR_INVALID, "n_dummy_scan must be resolved (>= 0): call swk_prepare");
+    if (p->seed == 0) return fail(e, SWK_ERR_INVALID, "seed must be non-zero (the caller resolves SEED = 0 like parameters::prepare)");
+    if (p->n_spins == 0) return fail(e, SWK_ERR_INVALID, "NUMBER_OF_SPINS must be positive");
+    CK(cudaSetDevice(e->device));
+
+    // ---- merged event timeline ----
+    struct Ev { int32_t time; uint32_t mask; };
+    std::vector<Ev> evs;
+    auto add = [&](const int32_t *tp, uint32_t n, uint32_t first, uint32_t bit) {
+        for (uint32_t i = first; i < n; i++) evs.push_back({tp[i], bit});
+    };
+    add(t->dephasing_tp, t->n_dephasing, 0, EV_DEPH);
+    add(t->gradient_tp, t->n_gradient, 0, EV_GRAD);
+    add(t->RF_tp, t->n_RF, 1, EV_RF); // pulse 0 is applied at the start of every TR (kernels.cu:117,125)
+    add(t->TE_tp, t->n_TE, 0, EV_ECHO);
+    std::stable_sort(evs.begin(), evs.end(), [](const Ev &a, const Ev &b) { return a.time < b.time; });
+    std::vector<int32_t> tl_time;
+    std::vector<uint32_t> tl_mask;
+    for (const Ev &v : evs) {
+        if (!tl_time.empty() && tl_time.back() == v.time) tl_mask.back() |= v.mask;
+        else { tl_time.push_back(v.time); tl_mask.push_back(v.mask); }
+    }
+
+    // ---- tables: double-precision sin/cos of the flip angles (kernels.cuh:203-206), T1/T2 in seconds ----
+    std::vector<float> rf_s(t->n_RF), rf_c(t->n_RF), T1s(ns), T2s(ns);
+    for (uint32_t i = 0; i < t->n_RF; i++) {
+        rf_s[i] = (float)sin(t->RF_FA_deg[i] * kDeg2Rad);
+        rf_c[i] = (float)cos(t->RF_FA_deg[i] * kDeg2Rad);
+    }
+    for (uint32_t i = 0; i < ns; i++) {
+        T1s[i] = (float)(t->T1_ms[i] * 1e-3); // kernels.cu:167-168
+        T2s[i] = (float)(t->T2_ms[i] * 1e-3);
+    }
+    std::vector<uint8_t> b;
+    BlobLayout L{};
+    const float zero = 0.f;
+    L.n_tl = (uint32_t)tl_time.size();
+    L.tl_time = put(b, tl_time.empty() ? (const void *)&zero : tl_time.data(), tl_time.size() * 4);
+    L.tl_mask = put(b, tl_mask.empty() ? (const void *)&zero : tl_mask.data(), tl_mask.size() * 4);
+    L.n_rf = t->n_RF;
+    L.rf_s = put(b, rf_s.data(), rf_s.size() * 4);
+    L.rf_c = put(b, rf_c.data(), rf_c.size() * 4);
+    L.rf_ph = put(b, t->RF_PH_deg, t->n_RF * 4);
+    L.n_deph = t->n_dephasing;
+    L.deph_deg = put(b, t->dephasing_deg ? (const void *)t->dephasing_deg : &zero, t->n_dephasing * 4);
+    L.n_grad = t->n_gradient;
+    L.gx = put(b, t->gradX_mTm ? (const void *)t->gradX_mTm : &zero, t->n_gradient * 4);
+    L.gy = put(b, t->gradY_mTm ? (const void *)t->gradY_mTm : &zero, t->n_gradient * 4);
+    L.gz = put(b, t->gradZ_mTm ? (const void *)t->gradZ_mTm : &zero, t->n_gradient * 4);
+    L.n_sub = ns;
+    L.sigma = put(b, t->step_sigma_m, ns * 8);
+    L.T1s = put(b, T1s.data(), ns * 4);
+    L.T2s = put(b, T2s.data(), ns * 4);
+    L.pXY = put(b, t->pXY, ns * ns * 4);
+    while (b.size() % 16) b.push_back(0);
+    L.bytes = (uint32_t)b.size();
+
+    int rc;
+    if ((rc = ensure(e, e->blob, b.size())) != SWK_OK) return rc;
+    CK(cudaMemcpyAsync(e->blob.p, b.data(), b.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->blob_h.swap(b);
+    e->L = L;
+    e->P = *p;
+    e->n_te = t->n_TE;
+    e->rf_ph0 = t->RF_PH_deg[0];
+    e->trj = p->record_trajectory ? (uint64_t)p->n_timepoints * (uint64_t)(p->n_dummy_scan + 1) : 1;
+    e->has_sequence = true;
+    return SWK_OK;
+}
+
+int swk_set_spins(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_first, uint32_t n_local)
+{
+    if (!e) return SWK_ERR_INVALID;
+    if (n_local == 0) return fail(e, SWK_ERR_INVALID, "swk_set_spins: n_local must be positive");
+    if (!XYZ0 && (!e->has_phantom || !e->has_sequence))
+        return fail(e, SWK_ERR_STATE, "swk_set_spins: device-side positions need the phantom (FoV) and the sequence (seed) first");
+    CK(cudaSetDevice(e->device));
+    int rc;
+    const size_t bytes = (size_t)n_local * 3 * sizeof(float);
+    if ((rc = ensure(e, e->xyz0, bytes)) != SWK_OK) return rc;
+    if (XYZ0) {
+        CK(cudaMemcpyAsync(e->xyz0.p, XYZ0, bytes, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        init_positions_kernel<<<(n_local + 255) / 256, 256, 0, e->stream>>>(static_cast<float *>(e->xyz0.p), n_local, spin_first, e->P.seed,
+                                                                           e->fov[0], e->fov[1], e->fov[2]);
+        CK(cudaGetLastError());
+    }
+    e->has_m0 = (M0 != nullptr);
+    if (M0) {
+        if ((rc = ensure(e, e->m0, bytes)) != SWK_OK) return rc;
+        CK(cudaMemcpyAsync(e->m0.p, M0, bytes, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        release(e->m0);
+    }
+    CK(cudaStreamSynchronize(e->stream)); // the caller may reuse its host buffers
+    e->spin_first = spin_first;
+    e->n_local = n_local;
+    e->has_spins = true;
+    return SWK_OK;
+}
+
+int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags, double *d_sums)
+{
+    if (!e) return SWK_ERR_INVALID;
+    if (!e->has_phantom) return fail(e, SWK_ERR_STATE, "swk_run_device: no phantom (swk_set_phantom)");
+    if (!e->has_sequence) return fail(e, SWK_ERR_STATE, "swk_run_device: no sequence (swk_set_sequence)");
+    if (!e->has_spins) return fail(e, SWK_ERR_STATE, "swk_run_device: no spins (swk_set_spins)");
+    if (!scales || n_scales == 0) return fail(e, SWK_ERR_INVALID, "swk_run_device: at least one scale is required");
+    if (scale_type < SWK_SCALE_FOV || scale_type > SWK_SCALE_PHASE_CYCLING) return fail(e, SWK_ERR_INVALID, "WHAT_TO_SCALE must be 0, 1 or 2");
+    if (mode != SWK_MODE_COMPAT && mode != SWK_MODE_FAST) return fail(e, SWK_ERR_INVALID, "unknown mode");
+    if (e->mask_substrates > e->P.n_substrate) { // monte_carlo.cu:113-118
+        char msg[200];
+        snprintf(msg, sizeof msg, "the number of substrate types in the mask does not match the config: %u vs %u", e->mask_substrates,
+                 e->P.n_substrate);
+        return fail(e, SWK_ERR_SUBSTRATE, msg);
+    }
+    if ((uint64_t)e->spin_first + e->n_local > e->P.n_spins) return fail(e, SWK_ERR_INVALID, "spin shard exceeds the global number of spins");
+    for (uint32_t i = 0; i < n_scales; i++)
+        if (scale_type == SWK_SCALE_FOV && !(scales[i] > 0.f)) return fail(e, SWK_ERR_INVALID, "FoV scales must be positive");
+    CK(cudaSetDevice(e->device));
+
+    const size_t K = n_scales, S = e->n_local, E = e->n_te, ns = e->P.n_substrate;
+    int rc;
+    if ((rc = ensure(e, e->scales, K * sizeof(float))) != SWK_OK) return rc;
+    if ((rc = ensure(e, e->M1, (flags & SWK_OUT_M1) ? K * S * E * 3 * sizeof(float) : 0)) != SWK_OK) return rc;
+    if ((rc = ensure(e, e->XYZ1, (flags & SWK_OUT_XYZ1) ? K * S * e->trj * 3 * sizeof(float) : 0)) != SWK_OK) return rc;
+    if ((rc = ensure(e, e->T, (flags & SWK_OUT_T) ? K * S * E : 0)) != SWK_OK) return rc;
+    if ((rc = ensure(e, e->sums, std::max<size_t>(K * E * ns * 4, 1) * sizeof(double))) != SWK_OK) return rc;
+    if ((rc = ensure(e, e->counters, 8 * sizeof(unsigned long long))) != SWK_OK) return rc;
+    double *sums = d_sums ? d_sums : static_cast<double *>(e->sums.p);
+
+    CK(cudaMemcpyAsync(e->scales.p, scales, K * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaEventRecord(e->evA, e->stream));
+    // outputs start at zero: lost spins / unwritten echoes read back as 0 (monte_carlo.cu:256,259-260)
+    if (e->M1.p) CK(cudaMemsetAsync(e->M1.p, 0, e->M1.bytes, e->stream));
+    if (e->XYZ1.p) CK(cudaMemsetAsync(e->XYZ1.p, 0, e->XYZ1.bytes, e->stream));
+    if (e->T.p) CK(cudaMemsetAsync(e->T.p, 0, e->T.bytes, e->stream));
+    if (E * ns) CK(cudaMemsetAsync(sums, 0, K * E * ns * 4 * sizeof(double), e->stream));
+    CK(cudaMemsetAsync(e->counters.p, 0, e->counters.bytes, e->stream));
+
+    WalkArgs A{};
+    A.mask = static_cast<const uint8_t *>(e->mask.p);
+    A.fieldmap = static_cast<const float *>(e->fieldmap.p);
+    A.nx = (uint32_t)e->dims[0]; A.ny = (uint32_t)e->dims[1]; A.nz = (uint32_t)e->dims[2];
+    A.V = (int64_t)(e->dims[0] * e->dims[1] * e->dims[2]);
+    for (int i = 0; i < 3; i++) A.fov[i] = e->fov[i];
+    A.c = e->P.c; A.s = e->P.s;
+    A.lin_pc = e->P.linear_phase_cycling; A.quad_pc = e->P.quadratic_phase_cycling;
+    A.rf_ph0 = e->rf_ph0;
+    A.field_k = e->P.B0 * e->P.timestep_us * 1e-6 * kGamma * kRad2Deg; // monte_carlo.cu:241
+    A.timestep_us = e->P.timestep_us;
+    A.n_tp = e->P.n_timepoints;
+    A.n_scans = (uint32_t)e->P.n_dummy_scan + 1u;
+    A.n_spins_global = e->P.n_spins;
+    A.n_te = e->n_te;
+    A.seed = e->P.seed;
+    A.max_iter = e->P.max_iterations;
+    A.cross_fov = e->P.cross_fov;
+    A.record = e->P.record_trajectory;
+    A.blob = static_cast<const uint8_t *>(e->blob.p);
+    A.L = e->L;
+    A.scales = static_cast<const float *>(e->scales.p);
+    A.n_scales = n_scales;
+    A.scale_type = scale_type;
+    A.xyz0 = static_cast<const float *>(e->xyz0.p);
+    A.m0 = e->has_m0 ? static_cast<const float *>(e->m0.p) : nullptr;
+    A.order = nullptr;
+    A.spin_first = e->spin_first;
+    A.n_local = e->n_local;
+    A.M1 = static_cast<float *>(e->M1.p);
+    A.XYZ1 = static_cast<float *>(e->XYZ1.p);
+    A.T = static_cast<uint8_t *>(e->T.p);
+    A.sums = (E * ns) ? sums : nullptr;
+    A.counters = static_cast<unsigned long long *>(e->counters.p);
+    A.trj = e->trj;
+
+    // shared memory: sequence tables (when they fit) + block sums
+    const size_t bsum_bytes = A.sums ? E * ns * 4 * sizeof(float) : 0;
+    const size_t smem_cap = std::min<size_t>(e->smem_optin, 96 * 1024);
+    if (bsum_bytes > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
+    A.blob_in_smem = (e->L.bytes + bsum_bytes <= smem_cap) ? 1 : 0;
+    const size_t smem = (A.blob_in_smem ? e->L.bytes : 0) + bsum_bytes;
+
+    const bool stats_on = (flags & SWK_RUN_STATS) != 0;
+    void (*kern)(const WalkArgs) = nullptr;
+    if (mode == SWK_MODE_COMPAT) kern = stats_on ? walk_kernel<SWK_MODE_COMPAT, true> : walk_kernel<SWK_MODE_COMPAT, false>;
+    else kern = stats_on ? walk_kernel<SWK_MODE_FAST, true> : walk_kernel<SWK_MODE_FAST, false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+
+    const uint64_t chunks = (S + kBlock - 1) / kBlock;
+    const uint64_t grid = chunks * K;
+    if (grid > 0x7fffffffull) return fail(e, SWK_ERR_INVALID, "too many spins x scales for one launch");
+    CK(cudaEventRecord(e->ev0, e->stream));
+    kern<<<(unsigned)grid, kBlock, smem, e->stream>>>(A);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev1, e->stream));
+    unsigned long long cnt[8] = {0};
+    CK(cudaMemcpyAsync(cnt, e->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream)); // ≙ the device sync after the launch (monte_carlo.cu:333)
+    float ms = 0.f, ms_all = 0.f;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    CK(cudaEventElapsedTime(&ms_all, e->evA, e->ev1));
+
+    e->n_scales = n_scales;
+    e->out_flags = flags;
+    e->last_sums = A.sums;
+    swk_stats &st = e->stats;
+    st = swk_stats{};
+    const uint64_t nominal = (uint64_t)S * K * A.n_scans * A.n_tp;
+    st.steps = stats_on ? cnt[0] : nominal;
+    st.mask_gathers = cnt[1];
+    st.field_gathers = cnt[2];
+    st.rejects = cnt[3];
+    st.lost = cnt[4];
+    st.kernel_ms = ms;
+    st.device_ms = ms_all;
+    st.n_launches = 1;
+    return SWK_OK;
+}
+
+int swk_download(swk_engine *e, float *M1, float *XYZ1, uint8_t *T)
+{
+    if (!e) return SWK_ERR_INVALID;
+    if (e->n_scales == 0) return fail(e, SWK_ERR_STATE, "swk_download: nothing has been run");
+    if ((M1 && !e->M1.p) || (XYZ1 && !e->XYZ1.p) || (T && !e->T.p)) return fail(e, SWK_ERR_STATE, "swk_download: output was not requested in the run flags");
+    CK(cudaSetDevice(e->device));
+    if (M1) CK(cudaMemcpyAsync(M1, e->M1.p, e->M1.bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (XYZ1) CK(cudaMemcpyAsync(XYZ1, e->XYZ1.p, e->XYZ1.bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (T) CK(cudaMemcpyAsync(T, e->T.p, e->T.bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SWK_OK;
+}
+
+int swk_get_sums(swk_engine *e, double *sums)
+{
+    if (!e || !sums) return SWK_ERR_INVALID;
+    if (e->n_scales == 0) return fail(e, SWK_ERR_STATE, "swk_get_sums: nothing has been run");
+    const size_t n = (size_t)e->n_scales * e->n_te * e->P.n_substrate * 4;
+    if (n == 0) return SWK_OK;
+    if (!e->last_sums) return fail(e, SWK_ERR_STATE, "swk_get_sums: no sums were accumulated");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(sums, e->last_sums, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SWK_OK;
+}
+
+int swk_get_stats(swk_engine *e, swk_stats *out)
+{
+    if (!e || !out) return SWK_ERR_INVALID;
+    *out = e->stats;
+    return SWK_OK;
+}
+
+int swk_run(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_first, uint32_t n_local, const float *scales, uint32_t n_scales,
+            int scale_type, int mode, float *M1, float *XYZ1, uint8_t *T, double *sums, swk_stats *stats)
+{
+    if (!e) return SWK_ERR_INVALID;
+    int rc;
+    if ((rc = swk_set_spins(e, XYZ0, M0, spin_first, n_local)) != SWK_OK) return rc;
+    const int flags = (M1 ? SWK_OUT_M1 : 0) | (XYZ1 ? SWK_OUT_XYZ1 : 0) | (T ? SWK_OUT_T : 0) | (stats ? SWK_RUN_STATS : 0);
+    if ((rc = swk_run_device(e, scales, n_scales, scale_type, mode, flags, nullptr)) != SWK_OK) return rc;
+    if ((rc = swk_download(e, M1, XYZ1, T)) != SWK_OK) return rc;
+    if (sums && (rc = swk_get_sums(e, sums)) != SWK_OK) return rc;
+    if (stats) *stats = e->stats;
+    return SWK_OK;
+}
+
+void *swk_stream(swk_engine *e) { return e ? (void *)e->stream : nullptr; }
+double *swk_device_sums(swk_engine *e) { return e ? e->last_sums : nullptr; }
+uint64_t swk_device_bytes(const swk_engine *e)
+{
+    if (!e) return 0;
+    uint64_t n = 0;
+    for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->blob, &e->xyz0, &e->m0, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters})
+        n += b->bytes;
+    return n;
+}
+
+} // extern "C"

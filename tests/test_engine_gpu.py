@@ -1,0 +1,200 @@
+"""GPU parity tests: the CUDA engine, called through the C-ABI (ctypes -> libspinwalk_b200.so), against
+  (1) the reference's own cu_sim kernel compiled for sm_100a (oracle/_ref/libswref_cuda.so) on the same GPU,
+  (2) the CPU oracle (oracle/sim_oracle.c),
+on the same seeded inputs.  Bars:
+  T (tissue index at echo)        bit-exact   (COMPAT mode vs reference cu_sim)
+  XYZ1 (positions / trajectories) bit-exact   (COMPAT mode vs reference cu_sim)
+  M1 (magnetisation)              |diff| <= 2e-6 absolute (FP32 round-off of the event math; the walk itself is exact)
+  FAST mode (Philox)              ensemble means within 4.5 combined standard errors of the oracle's
+"""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+M1_TOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def sw(engine_lib):
+    import spinwalk_b200 as sw
+
+    assert engine_lib.swk_device_count() > 0, "no CUDA device visible: GPU tests must not fall back to anything"
+    return sw
+
+
+def _run_engine(sw, case, mask, fm, fov, xyz0, mode, **kw):
+    cfg = cases.to_simconfig(case)
+    with sw.Engine(0) as e:
+        e.set_phantom(mask, fm, fov)
+        e.set_sequence(cfg)
+        return e.run(xyz0, mode=mode, **kw)
+
+
+@pytest.mark.parametrize("name", list(cases.ALL))
+def test_compat_bit_exact_vs_reference_cu_sim(sw, oracle, name):
+    """Engine (COMPAT arithmetic) == the reference's cu_sim launched on the same device."""
+    if not oracle.have_ref_cuda():
+        pytest.skip("oracle/_ref/libswref_cuda.so not present")
+    case, mask, fm, fov, xyz0 = cases.ALL[name]()
+    ref = oracle.run_ref_cuda(case, fm, mask, xyz0)
+    got = _run_engine(sw, case, mask, fm, fov, xyz0, sw.MODE_COMPAT)
+    assert np.array_equal(got["T"], ref["T"]), "tissue index at echo differs"
+    assert np.array_equal(got["XYZ1"].view(np.uint32), ref["XYZ1"].view(np.uint32)), "positions differ bitwise"
+    d = np.abs(got["M1"] - ref["M1"]).max()
+    assert d <= M1_TOL, f"max |dM1| = {d}"
+
+
+@pytest.mark.parametrize("name", list(cases.ALL))
+def test_compat_vs_cpu_oracle(sw, oracle, name):
+    """Engine (COMPAT) vs the CPU oracle, minstd flavour.  Host erfcinvf (double based) and libdevice erfcinvf
+    differ by ulps, so positions drift apart by ~1e-12 m and once in ~1e6 steps a spin sees the neighbouring
+    voxel for a step (another field sample, or another permeability outcome).  Bar: >= 99% of (scale, spin)
+    pairs have the same tissue at every echo, positions within 1e-9 m and M1 within 2e-4."""
+    case, mask, fm, fov, xyz0 = cases.ALL[name]()
+    ora = oracle.run_oracle(case, fm, mask, xyz0, flavour=oracle.RNG_MINSTD)
+    got = _run_engine(sw, case, mask, fm, fov, xyz0, sw.MODE_COMPAT)
+    same = ((got["T"] == ora["T"]).all(axis=2) & (np.abs(got["XYZ1"] - ora["XYZ1"]).max(axis=(2, 3)) < 1e-9)
+            & (np.abs(got["M1"] - ora["M1"]).max(axis=(2, 3)) <= 2e-4))
+    assert same.mean() >= 0.99, f"only {same.mean():.4f} of (scale, spin) pairs follow the oracle"
+    # work counters agree with the oracle's to the same extent
+    st, so = got["stats"], ora["stats"]
+    assert st["steps"] == pytest.approx(so["steps"], rel=2e-3)
+    assert st["mask_gathers"] == pytest.approx(so["mask_gathers"], rel=5e-3, abs=5)
+    assert st["rejects"] == pytest.approx(so["rejects"], rel=2e-2, abs=5)
+    assert st["lost"] == pytest.approx(so["lost"], abs=max(2, 0.01 * so["lost"]))
+
+
+def _ensemble(M1, T, sub=None):
+    """mean and standard error of Mx, My, Mz per (scale, echo) [optionally restricted to a substrate]."""
+    w = np.ones(T.shape, bool) if sub is None else (T == sub)
+    n = np.maximum(w.sum(axis=1), 1)[..., None]  # [K,E,1]
+    m = (M1 * w[..., None]).sum(axis=1) / n
+    v = ((M1 - m[:, None]) ** 2 * w[..., None]).sum(axis=1) / n
+    return m, np.sqrt(v / n), w.mean(axis=1)
+
+
+@pytest.mark.parametrize("name,n_spins", [("gre", 6000), ("se", 6000), ("pgse", 6000), ("ssfp", 2000), ("multi_echo", 6000)])
+def test_fast_mode_ensemble_vs_oracle(sw, oracle, name, n_spins):
+    """FAST mode (Philox + Box-Muller + FP32 grid coordinates) is a different random stream, so parity is
+    statistical: per (scale, echo, component) |mean_fast - mean_oracle| <= 4.5 sqrt(SE_fast^2 + SE_oracle^2),
+    plus an absolute floor of 2e-3 for nearly deterministic components, and the same tissue occupancy."""
+    case, mask, fm, fov, xyz0 = cases.ALL[name](n_spins=n_spins)
+    ora = oracle.run_oracle(case, fm, mask, xyz0, flavour=oracle.RNG_MT19937)
+    got = _run_engine(sw, case, mask, fm, fov, xyz0, sw.MODE_FAST)
+    assert got["stats"]["lost"] == 0
+    mo, so, oo = _ensemble(ora["M1"], ora["T"])
+    mg, sg, og = _ensemble(got["M1"], got["T"])
+    tol = 4.5 * np.sqrt(so**2 + sg**2) + 2e-3
+    assert (np.abs(mo - mg) <= tol).all(), f"ensemble mismatch: max excess {(np.abs(mo - mg) - tol).max()}"
+    for sub in range(case.n_substrate):
+        _, _, fo = _ensemble(ora["M1"], ora["T"], sub)
+        _, _, fg = _ensemble(got["M1"], got["T"], sub)
+        assert np.abs(fo - fg).max() <= 4.5 * np.sqrt(0.25 / n_spins * 2) + 1e-3
+    # step-size statistics: rms displacement per axis matches (free-ish diffusion at the largest scale)
+    k = int(np.argmax(case.scales)) if case.scale_type == oracle.SCALE_FOV else 0
+    s = case.scales[k] if case.scale_type == oracle.SCALE_FOV else 1.0
+    do = ora["XYZ1"][k, :, -1, :] - xyz0 * np.float32(s)
+    dg = got["XYZ1"][k, :, -1, :] - xyz0 * np.float32(s)
+    if not case.cross_fov:
+        assert np.allclose(do.std(axis=0), dg.std(axis=0), rtol=0.08)
+
+
+def test_fast_rng_free_gradient_closed_form(sw, oracle):
+    """config/gradient.ini: D = 0, one 50 us gradient sample of 521.9377 mT/m at 10 ms => the transverse phase
+    at the echo is gamma*G*x*dt (2 pi per 900 um).  No RNG is involved, so FAST and COMPAT must agree with the
+    oracle to FP32 round-off and with the closed form to 1e-3 rad."""
+    case, mask, fm, fov, xyz0 = cases.gradient_rng_free()
+    ora = oracle.run_oracle(case, fm, mask, xyz0, flavour=oracle.RNG_MINSTD)
+    for mode in (sw.MODE_COMPAT, sw.MODE_FAST):
+        got = _run_engine(sw, case, mask, fm, fov, xyz0, mode)
+        assert np.abs(got["M1"] - ora["M1"]).max() <= (2e-6 if mode == sw.MODE_COMPAT else 2e-4)
+        ph = np.arctan2(got["M1"][0, :, 0, 1], got["M1"][0, :, 0, 0])
+        # RF 90 about y puts M along +x; phase advances by gamma*G*x*dt
+        expect = 267515315.0 * 521.9377e-3 * xyz0[:, 0].astype(np.float64) * 50e-6
+        dphi = np.angle(np.exp(1j * (ph - expect)))
+        assert np.abs(dphi).max() < 1e-3
+
+
+@pytest.mark.parametrize("mode_name", ["COMPAT", "FAST"])
+def test_sums_match_per_spin_outputs(sw, mode_name):
+    """the in-kernel ensemble sums [scale][echo][substrate][Mx,My,Mz,N] equal a host reduction of M1 / T."""
+    mode = getattr(sw, "MODE_" + mode_name)
+    case, mask, fm, fov, xyz0 = cases.multi_echo(n_spins=3000)
+    got = _run_engine(sw, case, mask, fm, fov, xyz0, mode)
+    K, E, ns = case.n_scales, case.n_TE, case.n_substrate
+    valid = (got["M1"] != 0).any(axis=3)  # lost / unwritten echoes stay zero
+    for sub in range(ns):
+        w = (got["T"] == sub) & valid
+        assert np.array_equal(got["sums"][:, :, sub, 3], w.sum(axis=1).astype(np.float64))
+        ref = (got["M1"].astype(np.float64) * w[..., None]).sum(axis=1)
+        assert np.allclose(got["sums"][:, :, sub, :3], ref, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("mode_name", ["COMPAT", "FAST"])
+def test_shards_are_invariant(sw, mode_name):
+    """RNG and the dephasing term are keyed by the GLOBAL spin id: simulating [0,n/2) and [n/2,n) on separate
+    engines gives exactly the arrays of the single run (what makes multi-GPU results independent of G)."""
+    mode = getattr(sw, "MODE_" + mode_name)
+    case, mask, fm, fov, xyz0 = cases.multi_echo(n_spins=1000)
+    cfg = cases.to_simconfig(case)
+    full = _run_engine(sw, case, mask, fm, fov, xyz0, mode)
+    parts = []
+    for first, n in ((0, 437), (437, 563)):
+        with sw.Engine(0) as e:
+            e.set_phantom(mask, fm, fov)
+            e.set_sequence(cfg)
+            parts.append(e.run(xyz0[first:first + n], spin_first=first, mode=mode))
+    for key in ("M1", "XYZ1", "T"):
+        cat = np.concatenate([p[key] for p in parts], axis=1)
+        assert np.array_equal(cat, full[key]), key
+    assert np.allclose(parts[0]["sums"] + parts[1]["sums"], full["sums"], rtol=1e-6, atol=1e-4)
+
+
+def test_device_resident_run_and_device_positions(sw):
+    """set_spins(NULL) draws positions on the device inside [1%,99%] of the FoV; run_device + download equals run()."""
+    case, mask, fm, fov, xyz0 = cases.gre(n_spins=2048, scales=(1.0,))
+    cfg = cases.to_simconfig(case)
+    with sw.Engine(0) as e:
+        e.set_phantom(mask, fm, fov)
+        e.set_sequence(cfg)
+        e.set_spins(xyz0)
+        st = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS)
+        m1, x1, t = e.download()
+        host = e.run(xyz0, mode=sw.MODE_FAST)
+        assert np.array_equal(m1, host["M1"]) and np.array_equal(t, host["T"]) and np.array_equal(x1, host["XYZ1"])
+        assert st["steps"] == case.total_steps() and st["n_launches"] == 1 and st["kernel_ms"] > 0
+        e.set_spins(None, n_local=2048)
+        e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_XYZ1)
+        _, x1, _ = e.download(M1=False, T=False)
+        assert np.isfinite(x1).all() and (x1 >= 0).all() and (x1 < np.asarray(fov)).all()
+
+
+def test_error_conventions(sw):
+    """bad inputs fail with a status + message (≙ the reference's `return false` + log line), never silently."""
+    case, mask, fm, fov, xyz0 = cases.gre(n_spins=64, scales=(1.0,))
+    cfg = cases.to_simconfig(case)
+    with sw.Engine(0) as e:
+        with pytest.raises(sw.EngineError, match="no phantom"):
+            e.set_sequence(cfg)
+            e.set_spins(xyz0)
+            e.run_device()
+        e.set_phantom(mask, fm, fov)
+        bad = cases.to_simconfig(case)
+        bad.RF_T_us = [50]
+        with pytest.raises(sw.EngineError, match="first RF start time"):
+            e.set_sequence(bad)
+        bad = cases.to_simconfig(case)
+        bad.TE_us = [20000, 10000]
+        with pytest.raises(sw.EngineError, match="ascending"):
+            e.set_sequence(bad)
+        one = cases.to_simconfig(case)
+        one.diffusivity, one.T1_ms, one.T2_ms, one.pXY = [1e-9], [1000.0], [50.0], [1.0]
+        e.set_sequence(one)
+        e.set_spins(xyz0)
+        with pytest.raises(sw.EngineError, match="substrate"):  # mask has 2 substrates, config 1 (monte_carlo.cu:113-118)
+            e.run_device()
+    with pytest.raises(sw.EngineError, match="not available"):
+        sw.Engine(999)
