@@ -17,7 +17,13 @@ ap.add_argument("--scales", type=str, default="0.0125,0.0641,0.2010,0.6309,1.030
 ap.add_argument("--modes", type=str, default="fast,compat")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--flags", type=int, default=sw.OUT_ALL)
+ap.add_argument("--nosort", action="store_true")
+ap.add_argument("--nopack", action="store_true")
 args = ap.parse_args()
+if args.nosort:
+    args.flags |= sw.RUN_NO_SORT
+if args.nopack:
+    args.flags |= sw.RUN_NO_PACK
 
 cfg_kw, ph, _ = bench.workload("c2", args.spins, None)
 ph["n"], ph["fov_um"] = args.n, float(args.n)

@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "engine.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", "walk_kernel.cuh"), os.path.join(HERE, "..", "include", "spinwalk_engine.h")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))] + [os.path.join(HERE, "..", "include", "spinwalk_engine.h")]
 OUT = os.path.join(HERE, "libspinwalk_b200.so")
 
 NVCC_FLAGS = [

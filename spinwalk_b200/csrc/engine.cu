@@ -13,6 +13,9 @@
 
 #include <cuda_runtime.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
+#include "walk_fast.cuh"
 #include "walk_kernel.cuh"
 
 using namespace swk;
@@ -37,7 +40,8 @@ struct swk_engine {
     size_t smem_optin = 0;
 
     // phantom
-    DevBuf mask, fieldmap;
+    DevBuf mask, fieldmap, packed;
+    bool packed_valid = false;
     uint64_t dims[3] = {0, 0, 0};
     float fov[3] = {0, 0, 0};
     uint32_t mask_substrates = 0;
@@ -52,7 +56,8 @@ struct swk_engine {
     bool has_sequence = false;
 
     // spins
-    DevBuf xyz0, m0;
+    DevBuf xyz0, m0, order;
+    bool order_valid = false;
     uint32_t spin_first = 0, n_local = 0;
     bool has_m0 = false, has_spins = false;
 
@@ -124,6 +129,45 @@ __global__ void mask_max_kernel(const uint8_t *mask, size_t n, unsigned int *out
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
+// ---- locality order of the spins -------------------------------------------------------------------------------
+// key = (255 - substrate of the start voxel) << 48 | 48-bit Morton code of the start voxel.  Warps then hold spins of one
+// substrate that start next to each other: (1) redraw loops behind impermeable walls (kernels.cu:154-160) no longer
+// idle the other lanes of a warp, (2) the mask / field sectors a warp gathers are shared in L1/L2.  The start voxel does
+// not depend on the FoV scale (positions and FoV scale together, monte_carlo.cu:278-280), so one order serves all scales.
+__device__ __forceinline__ uint64_t spread3(uint32_t v)
+{ // 16 bits -> every third bit
+    uint64_t x = v & 0xffffu;
+    x = (x | (x << 32)) & 0x00ff00000000ffffull;
+    x = (x | (x << 16)) & 0x00ff0000ff0000ffull;
+    x = (x | (x << 8)) & 0xf00f00f00f00f00full;
+    x = (x | (x << 4)) & 0x30c30c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x9249249249249249ull;
+    return x;
+}
+// Compact voxel word of SWK_MODE_FAST: the FP32 field (Tesla) rounded to 20 mantissa bits, substrate id in the 4 low bits.
+// One 4-byte gather per voxel change instead of a byte + a float from two arrays; relative field error <= 2^-21.
+__global__ void pack_voxels_kernel(const uint8_t *mask, const float *field, size_t n, uint32_t *out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t b = __float_as_uint(field[i]);
+        if ((b & 0x7f800000u) != 0x7f800000u) b += 8u; // round to nearest (carry into the exponent is still the right value)
+        out[i] = (b & 0xfffffff0u) | (uint32_t)mask[i];
+    }
+}
+
+__global__ void sort_keys_kernel(const float *xyz0, uint32_t n, const uint8_t *mask, uint32_t nx, uint32_t ny, uint32_t nz, float ihx,
+                                 float ihy, float ihz, uint64_t *keys, uint32_t *ids)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int vx = max(0, min((int)floorf(xyz0[3 * (size_t)j + 0] * ihx), (int)nx - 1));
+    const int vy = max(0, min((int)floorf(xyz0[3 * (size_t)j + 1] * ihy), (int)ny - 1));
+    const int vz = max(0, min((int)floorf(xyz0[3 * (size_t)j + 2] * ihz), (int)nz - 1));
+    const uint32_t ts = mask[((size_t)vx * ny + vy) * nz + vz];
+    keys[j] = ((uint64_t)(255u - ts) << 48) | (spread3(vx) << 2) | (spread3(vy) << 1) | spread3(vz);
+    ids[j] = j;
+}
+
 bool ascending(const int32_t *t, uint32_t n)
 {
     for (uint32_t i = 1; i < n; i++)
@@ -190,7 +234,7 @@ void swk_destroy(swk_engine *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
-    for (DevBuf *b : {&e->mask, &e->fieldmap, &e->blob, &e->xyz0, &e->m0, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters})
+    for (DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters})
         release(*b);
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -220,8 +264,11 @@ int swk_set_phantom(swk_engine *e, const uint8_t *mask, const float *fieldmap_T,
     CK(cudaSetDevice(e->device));
     const size_t V = (size_t)dims[0] * dims[1] * dims[2];
     e->has_phantom = false;
+    e->order_valid = false;
     release(e->mask); // ≙ cleanup_device (monte_carlo.cu:86-95)
     release(e->fieldmap);
+    release(e->packed);
+    e->packed_valid = false;
     int rc;
     if ((rc = ensure(e, e->mask, V)) != SWK_OK) return rc;
     if (fieldmap_T && (rc = ensure(e, e->fieldmap, V * sizeof(float))) != SWK_OK) return rc;
@@ -368,6 +415,7 @@ int swk_set_spins(swk_engine *e, const float *XYZ0, const float *M0, uint32_t sp
     e->spin_first = spin_first;
     e->n_local = n_local;
     e->has_spins = true;
+    e->order_valid = false;
     return SWK_OK;
 }
 
@@ -410,9 +458,52 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     if (E * ns) CK(cudaMemsetAsync(sums, 0, K * E * ns * 4 * sizeof(double), e->stream));
     CK(cudaMemsetAsync(e->counters.p, 0, e->counters.bytes, e->stream));
 
+    uint32_t extra_launches = 0;
+    if (flags & SWK_RUN_NO_SORT) {
+        release(e->order);
+        e->order_valid = false;
+    } else if (!e->order_valid) {
+        DevBuf keys_in, keys_out, ids_in, tmp;
+        int rs = SWK_OK;
+        size_t tmp_bytes = 0;
+        if ((rs = ensure(e, e->order, S * sizeof(uint32_t))) == SWK_OK && (rs = ensure(e, keys_in, S * 8)) == SWK_OK &&
+            (rs = ensure(e, keys_out, S * 8)) == SWK_OK && (rs = ensure(e, ids_in, S * 4)) == SWK_OK) {
+            sort_keys_kernel<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(
+                static_cast<const float *>(e->xyz0.p), (uint32_t)S, static_cast<const uint8_t *>(e->mask.p), (uint32_t)e->dims[0],
+                (uint32_t)e->dims[1], (uint32_t)e->dims[2], (float)e->dims[0] / e->fov[0], (float)e->dims[1] / e->fov[1],
+                (float)e->dims[2] / e->fov[2], static_cast<uint64_t *>(keys_in.p), static_cast<uint32_t *>(ids_in.p));
+            cudaError_t ce = cudaGetLastError();
+            if (ce == cudaSuccess)
+                ce = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, static_cast<uint64_t *>(keys_in.p), static_cast<uint64_t *>(keys_out.p),
+                                                     static_cast<uint32_t *>(ids_in.p), static_cast<uint32_t *>(e->order.p), (int)S, 0, 56, e->stream);
+            if (ce == cudaSuccess && (rs = ensure(e, tmp, tmp_bytes)) == SWK_OK)
+                ce = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, static_cast<uint64_t *>(keys_in.p), static_cast<uint64_t *>(keys_out.p),
+                                                     static_cast<uint32_t *>(ids_in.p), static_cast<uint32_t *>(e->order.p), (int)S, 0, 56, e->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+            if (ce != cudaSuccess) rs = fail(e, SWK_ERR_CUDA, std::string("spin ordering: ") + cudaGetErrorString(ce));
+        }
+        release(keys_in); release(keys_out); release(ids_in); release(tmp);
+        if (rs != SWK_OK) return rs;
+        e->order_valid = true;
+        extra_launches++;
+    }
+
+    // compact voxel words for the FAST walk (built once per phantom)
+    const bool want_packed = mode == SWK_MODE_FAST && e->fieldmap.p && e->mask_substrates <= 16 && !(flags & SWK_RUN_NO_PACK);
+    if (want_packed && !e->packed_valid) {
+        const size_t V = (size_t)(e->dims[0] * e->dims[1] * e->dims[2]);
+        if ((rc = ensure(e, e->packed, V * sizeof(uint32_t))) != SWK_OK) return rc;
+        pack_voxels_kernel<<<e->sm_count * 16, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), static_cast<const float *>(e->fieldmap.p), V,
+                                                                  static_cast<uint32_t *>(e->packed.p));
+        CK(cudaGetLastError());
+        e->packed_valid = true;
+        extra_launches++;
+    }
+
     WalkArgs A{};
     A.mask = static_cast<const uint8_t *>(e->mask.p);
     A.fieldmap = static_cast<const float *>(e->fieldmap.p);
+    A.packed = want_packed ? static_cast<const uint32_t *>(e->packed.p) : nullptr;
     A.nx = (uint32_t)e->dims[0]; A.ny = (uint32_t)e->dims[1]; A.nz = (uint32_t)e->dims[2];
     A.V = (int64_t)(e->dims[0] * e->dims[1] * e->dims[2]);
     for (int i = 0; i < 3; i++) A.fov[i] = e->fov[i];
@@ -436,7 +527,7 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     A.scale_type = scale_type;
     A.xyz0 = static_cast<const float *>(e->xyz0.p);
     A.m0 = e->has_m0 ? static_cast<const float *>(e->m0.p) : nullptr;
-    A.order = nullptr;
+    A.order = e->order_valid ? static_cast<const uint32_t *>(e->order.p) : nullptr;
     A.spin_first = e->spin_first;
     A.n_local = e->n_local;
     A.M1 = static_cast<float *>(e->M1.p);
@@ -450,13 +541,21 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     const size_t bsum_bytes = A.sums ? E * ns * 4 * sizeof(float) : 0;
     const size_t smem_cap = std::min<size_t>(e->smem_optin, 96 * 1024);
     if (bsum_bytes > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
-    A.blob_in_smem = (e->L.bytes + bsum_bytes <= smem_cap) ? 1 : 0;
-    const size_t smem = (A.blob_in_smem ? e->L.bytes : 0) + bsum_bytes;
+    A.blob_in_smem = (e->L.bytes + bsum_bytes + 3 * ns * sizeof(float) <= smem_cap) ? 1 : 0;
+    const size_t sgt_bytes = (mode == SWK_MODE_FAST) ? 3 * ns * sizeof(float) : 0;
+    const size_t smem = (A.blob_in_smem ? e->L.bytes : 0) + bsum_bytes + sgt_bytes;
+    if (mode == SWK_MODE_FAST && (uint64_t)A.V >= (1ull << 32)) return fail(e, SWK_ERR_INVALID, "SWK_MODE_FAST indexes voxels with 32 bits: phantom too large");
 
     const bool stats_on = (flags & SWK_RUN_STATS) != 0;
     void (*kern)(const WalkArgs) = nullptr;
     if (mode == SWK_MODE_COMPAT) kern = stats_on ? walk_kernel<SWK_MODE_COMPAT, true> : walk_kernel<SWK_MODE_COMPAT, false>;
-    else kern = stats_on ? walk_kernel<SWK_MODE_FAST, true> : walk_kernel<SWK_MODE_FAST, false>;
+    else {
+        const int vox = A.packed ? VOX_PACKED : (A.fieldmap ? VOX_SPLIT : VOX_MASK);
+#define SWK_PICK(V) (A.record ? (stats_on ? walk_fast_kernel<true, true, V> : walk_fast_kernel<false, true, V>) \
+                              : (stats_on ? walk_fast_kernel<true, false, V> : walk_fast_kernel<false, false, V>))
+        kern = vox == VOX_PACKED ? SWK_PICK(VOX_PACKED) : (vox == VOX_SPLIT ? SWK_PICK(VOX_SPLIT) : SWK_PICK(VOX_MASK));
+#undef SWK_PICK
+    }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
 
     const uint64_t chunks = (S + kBlock - 1) / kBlock;
@@ -486,7 +585,7 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     st.lost = cnt[4];
     st.kernel_ms = ms;
     st.device_ms = ms_all;
-    st.n_launches = 1;
+    st.n_launches = 1 + extra_launches;
     return SWK_OK;
 }
 
@@ -543,7 +642,7 @@ uint64_t swk_device_bytes(const swk_engine *e)
 {
     if (!e) return 0;
     uint64_t n = 0;
-    for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->blob, &e->xyz0, &e->m0, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters})
+    for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters})
         n += b->bytes;
     return n;
 }

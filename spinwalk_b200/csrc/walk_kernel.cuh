@@ -51,6 +51,7 @@ struct WalkArgs {
     // phantom
     const uint8_t *mask;
     const float   *fieldmap; // Tesla at 1 T, or nullptr
+    const uint32_t *packed;  // FAST mode: (field bits & ~15) | substrate, or nullptr
     uint32_t nx, ny, nz;
     int64_t  V;
     float    fov[3];         // metres (held as float like the reference, monte_carlo.cuh:37)

@@ -165,7 +165,7 @@ def test_device_resident_run_and_device_positions(sw):
         m1, x1, t = e.download()
         host = e.run(xyz0, mode=sw.MODE_FAST)
         assert np.array_equal(m1, host["M1"]) and np.array_equal(t, host["T"]) and np.array_equal(x1, host["XYZ1"])
-        assert st["steps"] == case.total_steps() and st["n_launches"] == 1 and st["kernel_ms"] > 0
+        assert st["steps"] == case.total_steps() and st["n_launches"] >= 1 and st["kernel_ms"] > 0
         e.set_spins(None, n_local=2048)
         e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_XYZ1)
         _, x1, _ = e.download(M1=False, T=False)
