@@ -1,41 +1,35 @@
-"""Summarise an `ncu --page source --csv --print-source sass` dump: hottest SASS ranges by executed instructions.
-usage: python scripts/sass_hot.py dump.csv [min_exec_frac]"""
+"""Summarise an `ncu -i X.ncu-rep --page source --csv --print-source sass [--launch-skip N --launch-count 1]` dump:
+hottest SASS address ranges by executed warp-instructions and stall samples.
+usage: python scripts/sass_hot.py dump.csv [min_share]"""
 import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
-hdr = rows[1]
-iA, iS, iE, iT, iSm = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Avg. Threads Executed"), hdr.index("# Samples")
-stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-data = rows[2:]
+hdr = next(r for r in rows if "Address" in r and "Source" in r)
+data = [r for r in rows if len(r) == len(hdr) and r[0].startswith("0x")]
+iA, iS, iE, iT, iSm = (hdr.index(k) for k in ("Address", "Source", "Instructions Executed", "Avg. Threads Executed", "# Samples"))
+thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.004
 tot = sum(int(r[iE]) for r in data)
 totS = sum(int(r[iSm]) for r in data)
-print(f"total warp-instructions {tot:.4g}, samples {totS}")
-thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
-# print every instruction with exec count, grouped into runs of equal count
-prev = None
-run = []
-def flush():
-    if not run: return
-    n = int(run[0][iE]); k = len(run)
-    if n * k / tot >= thr:
-        smp = sum(int(r[iSm]) for r in run)
-        st = {}
-        for r in run:
-            for c in stall_cols:
-                v = int(r[c] or 0)
-                if v: st[hdr[c]] = st.get(hdr[c], 0) + v
-        top = sorted(st.items(), key=lambda kv: -kv[1])[:3]
-        ops = {}
-        for r in run:
-            op = r[iS].split()[0] if not r[iS].strip().startswith("@") else r[iS].split()[1]
-            op = op.split(".")[0]
-            ops[op] = ops.get(op, 0) + 1
-        opss = " ".join(f"{o}x{c}" for o, c in sorted(ops.items(), key=lambda kv: -kv[1])[:8])
-        print(f"{run[0][iA][-5:]} n={k:4d} exec/instr={n:11d} share={n*k/tot:6.2%} samples={smp/totS:6.2%} thr={float(run[0][iT]):5.1f} | {opss} | {top}")
+print(f"warp-instructions {tot:.4g}, stall samples {totS}, SASS lines {len(data)}")
+base = int(data[0][iA], 16)
+groups, cur = [], []
 for r in data:
-    key = r[iE]
-    if prev is not None and key != prev:
-        flush(); run = []
-    run.append(r); prev = key
-flush()
+    n = int(r[iE])
+    if cur and abs(n - int(cur[-1][iE])) > 0.03 * max(n, int(cur[-1][iE]), 1):
+        groups.append(cur)
+        cur = []
+    cur.append(r)
+groups.append(cur)
+for g in groups:
+    n = sum(int(r[iE]) for r in g)
+    s = sum(int(r[iSm]) for r in g)
+    if n / tot < thr and s / totS < thr:
+        continue
+    ops = {}
+    for r in g:
+        t = r[iS].split()
+        op = (t[1] if t[0].startswith("@") else t[0]).split(".")[0]
+        ops[op] = ops.get(op, 0) + 1
+    print(f"{int(g[0][iA], 16) - base:5x}-{int(g[-1][iA], 16) - base:5x} n={len(g):3d} exec/ins={int(g[0][iE]):10d} share={n / tot:6.2%} "
+          f"samples={s / totS:6.2%} thr={sum(float(r[iT]) for r in g) / len(g):5.1f} | " + " ".join(f"{o}x{c}" for o, c in sorted(ops.items(), key=lambda kv: -kv[1])[:7]))
