@@ -214,6 +214,7 @@ def main():
     import torch.distributed as dist
 
     import spinwalk_b200 as sw
+    from spinwalk_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
@@ -230,7 +231,8 @@ def main():
     mask_d = torch.from_numpy(mask2).to(dev)[:, :, None].expand(n, n, n).contiguous()
     fm_d = torch.from_numpy(fm2).to(dev)[:, :, None].expand(n, n, n).contiguous()
 
-    spin_first = rank * S_per_gpu
+    spin_first, n_local = sharding.shard_range(S_per_gpu * world, rank, world)  # weak scaling: S_per_gpu spins on every rank
+    assert n_local == S_per_gpu
     xyz0_pin = torch.empty((S_per_gpu, 3), dtype=torch.float32, pin_memory=True)
     xyz0_pin.numpy()[:] = make_positions(S_per_gpu, fov, cfg.seed, spin_first)
 
@@ -250,8 +252,7 @@ def main():
 
     def one_pass():
         st = eng.run_device(mode=mode, flags=sw.OUT_ALL, d_sums_ptr=sums_d.data_ptr())
-        if world > 1:  # the one collective of the path: a few KB of per-echo ensemble sums
-            dist.all_reduce(sums_d, op=dist.ReduceOp.SUM)
+        sharding.allreduce_sums(sums_d)  # the one collective of the path: a few KB of per-echo ensemble sums (NCCL)
         return st
 
     # counters (voxel changes etc.) for the roofline's algorithmic bytes: same inputs, STATS kernel variant, untimed
@@ -294,7 +295,7 @@ def main():
             r = eng.run(xyz0_pin.numpy(), None, spin_first, mode=mode, out=out_np, stats=False)
             if world > 1:
                 sums_d.copy_(torch.from_numpy(r["sums"]))
-                dist.all_reduce(sums_d, op=dist.ReduceOp.SUM)
+                sharding.allreduce_sums(sums_d)
         barrier()
         e2e_s = time.perf_counter() - t0
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

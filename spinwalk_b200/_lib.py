@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libspinwalk_b200.so")
+# SPINWALK_B200_LIB selects another build of the SAME library (tuning experiments: launch bounds etc.)
+LIB_PATH = os.environ.get("SPINWALK_B200_LIB") or os.path.join(HERE, "libspinwalk_b200.so")
 
 SWK_OK, SWK_ERR_INVALID, SWK_ERR_CUDA, SWK_ERR_MEMORY, SWK_ERR_STATE, SWK_ERR_SUBSTRATE = range(6)
 SCALE_FOV, SCALE_GRADIENT, SCALE_PHASE_CYCLING = 0, 1, 2

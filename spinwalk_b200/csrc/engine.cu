@@ -34,6 +34,9 @@ struct DevBuf {
 struct swk_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t cstream[2] = {nullptr, nullptr}; // pipelined host runs: slices alternate between two compute streams
+    cudaStream_t dstream = nullptr;               // ... and their results are downloaded on this one
+    std::vector<cudaEvent_t> ev_slice;
     cudaEvent_t evA = nullptr, ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int sm_count = 0;
@@ -58,12 +61,13 @@ struct swk_engine {
     // spins
     DevBuf xyz0, m0, order;
     bool order_valid = false;
+    uint32_t order_slice = 0; // slice length the order was built for (0 = one slice)
     uint32_t spin_first = 0, n_local = 0;
     bool has_m0 = false, has_spins = false;
 
     // run state / outputs
     DevBuf scales, M1, XYZ1, T, sums, counters;
-    uint32_t n_scales = 0, n_te = 0;
+    uint32_t n_scales = 0, n_te = 0, last_slices = 1;
     uint64_t trj = 1;
     int out_flags = 0;
     double *last_sums = nullptr; // device pointer actually used by the last run
@@ -155,8 +159,10 @@ __global__ void pack_voxels_kernel(const uint8_t *mask, const float *field, size
     }
 }
 
+// With slice_len != 0 the slice number of the spin (id / slice_len) leads the key, so that the sorted order is slice-major
+// and a pipelined run can launch (and download) one contiguous id range after the other.
 __global__ void sort_keys_kernel(const float *xyz0, uint32_t n, const uint8_t *mask, uint32_t nx, uint32_t ny, uint32_t nz, float ihx,
-                                 float ihy, float ihz, uint64_t *keys, uint32_t *ids)
+                                 float ihy, float ihz, uint32_t slice_len, uint64_t *keys, uint32_t *ids)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -164,7 +170,8 @@ __global__ void sort_keys_kernel(const float *xyz0, uint32_t n, const uint8_t *m
     const int vy = max(0, min((int)floorf(xyz0[3 * (size_t)j + 1] * ihy), (int)ny - 1));
     const int vz = max(0, min((int)floorf(xyz0[3 * (size_t)j + 2] * ihz), (int)nz - 1));
     const uint32_t ts = mask[((size_t)vx * ny + vy) * nz + vz];
-    keys[j] = ((uint64_t)(255u - ts) << 48) | (spread3(vx) << 2) | (spread3(vy) << 1) | spread3(vz);
+    const uint64_t slice = slice_len ? j / slice_len : 0u;
+    keys[j] = (slice << 56) | ((uint64_t)(255u - ts) << 48) | (spread3(vx) << 2) | (spread3(vy) << 1) | spread3(vz);
     ids[j] = j;
 }
 
@@ -239,6 +246,9 @@ void swk_destroy(swk_engine *e)
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    for (cudaEvent_t ev : e->ev_slice) cudaEventDestroy(ev);
+    for (cudaStream_t st : {e->cstream[0], e->cstream[1], e->dstream})
+        if (st) cudaStreamDestroy(st);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -419,7 +429,15 @@ int swk_set_spins(swk_engine *e, const float *XYZ0, const float *M0, uint32_t sp
     return SWK_OK;
 }
 
-int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags, double *d_sums)
+// Host destinations of a pipelined run (swk_run): results of slice i are copied back while slice i+1 computes.
+struct HostOut {
+    float *M1 = nullptr;
+    float *XYZ1 = nullptr;
+    uint8_t *T = nullptr;
+};
+
+static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags, double *d_sums,
+                    uint32_t n_slices, const HostOut *host)
 {
     if (!e) return SWK_ERR_INVALID;
     if (!e->has_phantom) return fail(e, SWK_ERR_STATE, "swk_run_device: no phantom (swk_set_phantom)");
@@ -449,6 +467,24 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     if ((rc = ensure(e, e->counters, 8 * sizeof(unsigned long long))) != SWK_OK) return rc;
     double *sums = d_sums ? d_sums : static_cast<double *>(e->sums.p);
 
+    // ---- slices: contiguous id ranges launched one after the other (1 = the whole shard in one launch) ----
+    if (n_slices < 1) n_slices = 1;
+    uint32_t slice_len = (uint32_t)S;
+    if (n_slices > 1) {
+        slice_len = (uint32_t)(((S + n_slices - 1) / n_slices + kBlock - 1) / kBlock * kBlock);
+        n_slices = (uint32_t)((S + slice_len - 1) / slice_len);
+    }
+    if (n_slices > 1) {
+        for (int c = 0; c < 2; c++)
+            if (!e->cstream[c]) CK(cudaStreamCreateWithFlags(&e->cstream[c], cudaStreamNonBlocking));
+        if (!e->dstream) CK(cudaStreamCreateWithFlags(&e->dstream, cudaStreamNonBlocking));
+        while (e->ev_slice.size() < n_slices) {
+            cudaEvent_t ev;
+            CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->ev_slice.push_back(ev);
+        }
+    }
+
     CK(cudaMemcpyAsync(e->scales.p, scales, K * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(cudaEventRecord(e->evA, e->stream));
     // outputs start at zero: lost spins / unwritten echoes read back as 0 (monte_carlo.cu:256,259-260)
@@ -459,10 +495,11 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     CK(cudaMemsetAsync(e->counters.p, 0, e->counters.bytes, e->stream));
 
     uint32_t extra_launches = 0;
+    const uint32_t want_order_slice = n_slices > 1 ? slice_len : 0u;
     if (flags & SWK_RUN_NO_SORT) {
         release(e->order);
         e->order_valid = false;
-    } else if (!e->order_valid) {
+    } else if (!e->order_valid || e->order_slice != want_order_slice) {
         DevBuf keys_in, keys_out, ids_in, tmp;
         int rs = SWK_OK;
         size_t tmp_bytes = 0;
@@ -471,20 +508,21 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
             sort_keys_kernel<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(
                 static_cast<const float *>(e->xyz0.p), (uint32_t)S, static_cast<const uint8_t *>(e->mask.p), (uint32_t)e->dims[0],
                 (uint32_t)e->dims[1], (uint32_t)e->dims[2], (float)e->dims[0] / e->fov[0], (float)e->dims[1] / e->fov[1],
-                (float)e->dims[2] / e->fov[2], static_cast<uint64_t *>(keys_in.p), static_cast<uint32_t *>(ids_in.p));
+                (float)e->dims[2] / e->fov[2], want_order_slice, static_cast<uint64_t *>(keys_in.p), static_cast<uint32_t *>(ids_in.p));
             cudaError_t ce = cudaGetLastError();
             if (ce == cudaSuccess)
                 ce = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, static_cast<uint64_t *>(keys_in.p), static_cast<uint64_t *>(keys_out.p),
-                                                     static_cast<uint32_t *>(ids_in.p), static_cast<uint32_t *>(e->order.p), (int)S, 0, 56, e->stream);
+                                                     static_cast<uint32_t *>(ids_in.p), static_cast<uint32_t *>(e->order.p), (int)S, 0, 64, e->stream);
             if (ce == cudaSuccess && (rs = ensure(e, tmp, tmp_bytes)) == SWK_OK)
                 ce = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, static_cast<uint64_t *>(keys_in.p), static_cast<uint64_t *>(keys_out.p),
-                                                     static_cast<uint32_t *>(ids_in.p), static_cast<uint32_t *>(e->order.p), (int)S, 0, 56, e->stream);
+                                                     static_cast<uint32_t *>(ids_in.p), static_cast<uint32_t *>(e->order.p), (int)S, 0, 64, e->stream);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
             if (ce != cudaSuccess) rs = fail(e, SWK_ERR_CUDA, std::string("spin ordering: ") + cudaGetErrorString(ce));
         }
         release(keys_in); release(keys_out); release(ids_in); release(tmp);
         if (rs != SWK_OK) return rs;
         e->order_valid = true;
+        e->order_slice = want_order_slice;
         extra_launches++;
     }
 
@@ -545,6 +583,7 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     const size_t sgt_bytes = (mode == SWK_MODE_FAST) ? 3 * ns * sizeof(float) : 0;
     const size_t smem = (A.blob_in_smem ? e->L.bytes : 0) + bsum_bytes + sgt_bytes;
     if (mode == SWK_MODE_FAST && (uint64_t)A.V >= (1ull << 32)) return fail(e, SWK_ERR_INVALID, "SWK_MODE_FAST indexes voxels with 32 bits: phantom too large");
+    if (mode == SWK_MODE_FAST && std::max(A.nx, std::max(A.ny, A.nz)) > (1u << 20)) return fail(e, SWK_ERR_INVALID, "SWK_MODE_FAST: more than 2^20 voxels along one axis");
 
     const bool stats_on = (flags & SWK_RUN_STATS) != 0;
     void (*kern)(const WalkArgs) = nullptr;
@@ -558,16 +597,54 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
 
-    const uint64_t chunks = (S + kBlock - 1) / kBlock;
-    const uint64_t grid = chunks * K;
-    if (grid > 0x7fffffffull) return fail(e, SWK_ERR_INVALID, "too many spins x scales for one launch");
+    if ((((uint64_t)slice_len + kBlock - 1) / kBlock) * K > 0x7fffffffull) return fail(e, SWK_ERR_INVALID, "too many spins x scales for one launch");
     CK(cudaEventRecord(e->ev0, e->stream));
-    kern<<<(unsigned)grid, kBlock, smem, e->stream>>>(A);
-    CK(cudaGetLastError());
+    if (n_slices == 1) {
+        A.j_first = 0;
+        A.j_end = (uint32_t)S;
+        const uint64_t grid = ((S + kBlock - 1) / kBlock) * K;
+        kern<<<(unsigned)grid, kBlock, smem, e->stream>>>(A);
+        CK(cudaGetLastError());
+    } else {
+        // slice i runs on compute stream i & 1 (tails overlap the next slice); its rows are downloaded as soon as it is done
+        for (int c = 0; c < 2; c++) CK(cudaStreamWaitEvent(e->cstream[c], e->ev0, 0));
+        for (uint32_t i = 0; i < n_slices; i++) {
+            A.j_first = i * slice_len;
+            A.j_end = (uint32_t)std::min<size_t>(S, (size_t)(i + 1) * slice_len);
+            const uint64_t grid = (((uint64_t)(A.j_end - A.j_first) + kBlock - 1) / kBlock) * K;
+            kern<<<(unsigned)grid, kBlock, smem, e->cstream[i & 1]>>>(A);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e->ev_slice[i], e->cstream[i & 1]));
+        }
+        CK(cudaStreamWaitEvent(e->stream, e->ev_slice[n_slices - 1], 0));
+        CK(cudaStreamWaitEvent(e->stream, e->ev_slice[n_slices - 2], 0));
+    }
     CK(cudaEventRecord(e->ev1, e->stream));
     unsigned long long cnt[8] = {0};
     CK(cudaMemcpyAsync(cnt, e->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, e->stream));
+    if (host && n_slices > 1) { // rows [j_first, j_end) of every scale: one strided copy per array and slice
+        for (uint32_t i = 0; i < n_slices; i++) {
+            const size_t r0 = (size_t)i * slice_len, r1 = std::min<size_t>(S, r0 + slice_len);
+            CK(cudaStreamWaitEvent(e->dstream, e->ev_slice[i], 0));
+            if (host->M1 && e->M1.p) {
+                const size_t row = E * 3 * sizeof(float);
+                if (row) CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->M1) + r0 * row, S * row, static_cast<char *>(e->M1.p) + r0 * row, S * row,
+                                              (r1 - r0) * row, K, cudaMemcpyDeviceToHost, e->dstream));
+            }
+            if (host->XYZ1 && e->XYZ1.p) {
+                const size_t row = e->trj * 3 * sizeof(float);
+                CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->XYZ1) + r0 * row, S * row, static_cast<char *>(e->XYZ1.p) + r0 * row, S * row,
+                                     (r1 - r0) * row, K, cudaMemcpyDeviceToHost, e->dstream));
+            }
+            if (host->T && e->T.p) {
+                const size_t row = E;
+                if (row) CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->T) + r0 * row, S * row, static_cast<char *>(e->T.p) + r0 * row, S * row,
+                                              (r1 - r0) * row, K, cudaMemcpyDeviceToHost, e->dstream));
+            }
+        }
+    }
     CK(cudaStreamSynchronize(e->stream)); // ≙ the device sync after the launch (monte_carlo.cu:333)
+    if (host && n_slices > 1) CK(cudaStreamSynchronize(e->dstream));
     float ms = 0.f, ms_all = 0.f;
     CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     CK(cudaEventElapsedTime(&ms_all, e->evA, e->ev1));
@@ -575,6 +652,7 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     e->n_scales = n_scales;
     e->out_flags = flags;
     e->last_sums = A.sums;
+    e->last_slices = n_slices;
     swk_stats &st = e->stats;
     st = swk_stats{};
     const uint64_t nominal = (uint64_t)S * K * A.n_scans * A.n_tp;
@@ -585,8 +663,13 @@ int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int sc
     st.lost = cnt[4];
     st.kernel_ms = ms;
     st.device_ms = ms_all;
-    st.n_launches = 1 + extra_launches;
+    st.n_launches = n_slices + extra_launches;
     return SWK_OK;
+}
+
+int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags, double *d_sums)
+{
+    return run_impl(e, scales, n_scales, scale_type, mode, flags, d_sums, 1, nullptr);
 }
 
 int swk_download(swk_engine *e, float *M1, float *XYZ1, uint8_t *T)
@@ -629,8 +712,12 @@ int swk_run(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_fir
     int rc;
     if ((rc = swk_set_spins(e, XYZ0, M0, spin_first, n_local)) != SWK_OK) return rc;
     const int flags = (M1 ? SWK_OUT_M1 : 0) | (XYZ1 ? SWK_OUT_XYZ1 : 0) | (T ? SWK_OUT_T : 0) | (stats ? SWK_RUN_STATS : 0);
-    if ((rc = swk_run_device(e, scales, n_scales, scale_type, mode, flags, nullptr)) != SWK_OK) return rc;
-    if ((rc = swk_download(e, M1, XYZ1, T)) != SWK_OK) return rc;
+    // Large runs are cut into slices of >= 2^18 spins so that the device-to-host copy of slice i overlaps the walk of slice i+1.
+    const uint32_t n_slices = (M1 || XYZ1 || T) ? std::min<uint32_t>(16u, std::max<uint32_t>(1u, n_local >> 18)) : 1u;
+    HostOut host;
+    host.M1 = M1; host.XYZ1 = XYZ1; host.T = T;
+    if ((rc = run_impl(e, scales, n_scales, scale_type, mode, flags, nullptr, n_slices, &host)) != SWK_OK) return rc;
+    if (e->last_slices == 1 && (rc = swk_download(e, M1, XYZ1, T)) != SWK_OK) return rc; // small runs: plain download
     if (sums && (rc = swk_get_sums(e, sums)) != SWK_OK) return rc;
     if (stats) *stats = e->stats;
     return SWK_OK;

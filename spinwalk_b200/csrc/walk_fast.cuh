@@ -2,22 +2,25 @@
 //
 // Same stochastic process as the reference's time loop (src/sim/kernels.cu:107-232),
 // engineered for the B200 issue pipes instead of being a translation of it:
-//   * position = (voxel index, FP32 fraction of a voxel) per axis; a step is 3 FFMA; "did the voxel
-//     change" is three unsigned compares on the fraction bits (fraction still in [0,1) <=> no change),
-//     so the common no-change step touches neither the index arithmetic nor memory;
-//   * Philox4x32-10 with the ten round keys precomputed on the host and read as constant-bank
-//     operands (40 integer instructions per 128 random bits), Box-Muller on the MUFU pipe
-//     (lg2 / sqrt / sin / cos approx) — the random numbers for attempt n+1 are generated between
-//     ISSUING the mask/field gathers of attempt n and CONSUMING them, so the dependent-gather
-//     latency (L2 ~250 cyc, HBM ~600+ cyc) overlaps ~70 independent instructions per warp;
-//   * mask and field gathers of one voxel change are issued back to back (the reference's are
-//     dependent: mask -> permeability test -> field), through the read-only path;
-//   * per-thread time t: lanes of a warp re-converge only at sequence events, so a lane that has
-//     to redraw (permeability rejection, kernels.cu:154-160) does not stall the other 31 per step;
-//   * 32-bit voxel indices (V < 2^32), <= 64 registers => 4 CTAs (32 warps) per SM.
+//   * position = one 32-bit FIXED-POINT word per axis in grid units: voxel index in the high bits, FB fraction
+//     bits below.  A step is  pos += int(n * sigma)  done as one FFMA (magic-number rounding) + one IADD3;
+//     "did the voxel change" is (old ^ new) >> FB, so the common no-change step touches neither the index
+//     arithmetic nor memory, and there is no float<->int conversion (quarter-rate pipe) anywhere in the loop;
+//   * Philox4x32-10 with a fixed key: the ten round keys are immediates of the LOP3s (2 IMAD.WIDE + 2 LOP3 per
+//     round), Box-Muller on the MUFU pipe (lg2 / sqrt / sin / cos approx) — the random numbers of attempt n+1
+//     are generated between ISSUING the voxel gather of attempt n and CONSUMING it, so the gather latency
+//     (L2 ~250 cyc, HBM ~600+ cyc) overlaps ~65 independent instructions per warp;
+//   * one 4-byte gather per voxel change: the packed voxel word (FP32 field | 4-bit substrate id), read-only path;
+//   * per-thread time: lanes of a warp re-converge only at sequence events, so a lane that has to redraw
+//     (permeability rejection, kernels.cu:154-160) does not stall the other 31 per step;
+//   * 32-bit voxel indices (V < 2^32); registers kept low enough for >= 4 CTAs (32 warps) per SM.
 #pragma once
 
 #include "walk_kernel.cuh"
+
+#ifndef SWK_FAST_MIN_BLOCKS
+#define SWK_FAST_MIN_BLOCKS 5 // 48 registers: 40 warps per SM (measured best on the C2 mix of scales, profiles/)
+#endif
 
 namespace swk {
 
@@ -48,50 +51,60 @@ __device__ __forceinline__ uint4 philox_fixed(uint32_t c0, uint32_t c1, uint32_t
     return make_uint4(c0, c1, c2, c3);
 }
 
-// three N(0,1) from 128 random bits: Box-Muller, 23-bit uniforms, hardware transcendental approximations
+// three N(0,1) from 128 random bits: Box-Muller, 23-bit uniforms, hardware transcendental approximations.
+// |n| <= sqrt(2 ln 2^23) = 5.65 by construction (what bounds the fixed-point step below).
 __device__ __forceinline__ void normals3_fast(const uint4 r, float &n0, float &n1, float &n2)
 {
     const float kNeg2Ln2 = -1.3862943611198906f, k2Pi = 6.283185307179586f;
     const float ua = 2.0f - __uint_as_float((r.x >> 9) | 0x3f800000u); // (0,1]
     const float ub = 2.0f - __uint_as_float((r.z >> 9) | 0x3f800000u);
-    const float ta = __uint_as_float((r.y >> 9) | 0x3f800000u) - 1.0f; // [0,1)
-    const float tb = __uint_as_float((r.w >> 9) | 0x3f800000u) - 1.0f;
+    const float ta = fmaf(__uint_as_float((r.y >> 9) | 0x3f800000u), k2Pi, -k2Pi); // [0, 2 pi)
+    const float tb = fmaf(__uint_as_float((r.w >> 9) | 0x3f800000u), k2Pi, -k2Pi);
     const float ra = mufu_sqrt(kNeg2Ln2 * mufu_lg2(ua));
     const float rb = mufu_sqrt(kNeg2Ln2 * mufu_lg2(ub));
-    n0 = ra * mufu_cos(k2Pi * ta);
-    n1 = ra * mufu_sin(k2Pi * ta);
-    n2 = rb * mufu_cos(k2Pi * tb);
+    n0 = ra * mufu_cos(ta);
+    n1 = ra * mufu_sin(ta);
+    n2 = rb * mufu_cos(tb);
 }
 
-// FoV boundary of one axis (rare; out of line, arguments and result in registers).  kernels.cu:133-136
-struct FracVox { float g; int v; };
-__device__ __noinline__ FracVox fov_boundary(float g, int v, const float pf, const float d, const int pv, const int n, const int cross)
+// ---- fixed-point grid coordinates -------------------------------------------------------------------------------
+// pos = voxel << FB | fraction, FB chosen per launch-block (per scale) on the host side of the kernel:
+//   (a) 5.65 sigma_vox 2^FB < 2^22   so that the magic-number rounding of the step is exact to one unit,
+//   (b) (n + 1) 2^FB + 2^22 <= 2^32  so that a step across the far wall cannot wrap to a valid position;
+// a step below 0 wraps to >= 2^32 - 2^22, which (b) keeps above every valid position: both walls are caught by ONE
+// unsigned compare of the voxel index against n.
+constexpr float kMagic = 12582912.0f;           // 1.5 * 2^23: float(x + kMagic) holds round(x) in its low mantissa bits
+constexpr uint32_t kMagicBits = 0x4B400000u;
+
+__device__ __forceinline__ uint32_t fx_step(uint32_t pos, float n, float sg)
 {
-    if (cross) { // periodic: re-enter from the other side
-        v %= n;
-        if (v < 0) v += n;
-    } else { // the reference reverses the step: new = old - rnd
-        const float h = pf - d;
-        const int k = __float2int_rd(h);
-        g = h - (float)k;
-        v = pv + k;
-        if ((unsigned)v >= (unsigned)n) { g = pf; v = pv; } // |step| exceeds the distance to both walls: stay
-    }
-    return FracVox{g, v};
+    return pos + (uint32_t)__float_as_int(fmaf(n, sg, kMagic)) - kMagicBits;
 }
 
-// one axis of a voxel change: g = fraction + step lies outside [0,1).  (A fraction that rounds to exactly 1.0f is
-// kept as is: it is flagged as a change again on the next step and resolves itself.)
-__device__ __forceinline__ void hop_axis(float &g, int &v, const float pf, const float d, const int pv, const int n, const int cross)
+// FoV boundary of one axis (rare; out of line).  kernels.cu:133-136.  `q` is the tentative position, already outside [0, n).
+__device__ __noinline__ uint32_t fov_boundary(uint32_t q, const uint32_t p, const uint32_t n, const uint32_t fb, const int cross)
 {
-    const int k = __float2int_rd(g);
-    g -= (float)k;
-    v = pv + k;
-    if ((unsigned)v >= (unsigned)n) {
-        const FracVox r = fov_boundary(g, v, pf, d, pv, n, cross);
-        g = r.g;
-        v = r.v;
+    const uint32_t span = n << fb;
+    if (cross) { // periodic: re-enter from the other side (single wrap, like the reference)
+        q = ((int32_t)(q - p) < 0) ? q + span : q - span;
+    } else {     // the reference reverses the step: new = old - rnd
+        q = p - (q - p);
     }
+    if ((q >> fb) >= n) q = p; // |step| exceeds the distance to both walls: stay
+    return q;
+}
+
+// The voxel gather.  A plain ld.global.nc makes L2 fetch the whole 128 B line from HBM (measured: 3.7 sectors per
+// missed sector, tools/gather_probe.cu); the L2::64B prefetch-size qualifier halves that traffic at the same gather rate.
+__device__ __forceinline__ uint32_t ldg_voxel(const uint32_t *p)
+{
+#ifdef SWK_GATHER_L2_64B
+    uint32_t v;
+    asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
 }
 
 // VOX selects how a voxel is fetched: 0 = mask only (no fieldmap), 1 = mask byte + FP32 field (two gathers issued
@@ -99,7 +112,7 @@ __device__ __forceinline__ void hop_axis(float &g, int &v, const float pf, const
 enum { VOX_MASK = 0, VOX_SPLIT = 1, VOX_PACKED = 2 };
 
 template <bool STATS, bool RECORD, int VOX>
-__global__ void __launch_bounds__(kBlock, 4) walk_fast_kernel(const __grid_constant__ WalkArgs A)
+__global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(const __grid_constant__ WalkArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlobLayout &L = A.L;
@@ -117,7 +130,7 @@ __global__ void __launch_bounds__(kBlock, 4) walk_fast_kernel(const __grid_const
     }
     float *bsum = reinterpret_cast<float *>(smem + smem_used);
     const uint32_t n_bsum = A.sums ? A.n_te * L.n_sub * 4u : 0u;
-    // per-substrate step sigma in grid units for this block's scale: sgt[sub][axis]
+    // per-substrate step sigma in fixed-point grid units for this block's scale: sgt[sub][axis]
     float *sgt = bsum + n_bsum;
     for (uint32_t i = threadIdx.x; i < n_bsum; i += kBlock) bsum[i] = 0.f;
 
@@ -128,53 +141,64 @@ __global__ void __launch_bounds__(kBlock, 4) walk_fast_kernel(const __grid_const
     else if (A.scale_type == SWK_SCALE_GRADIENT) gscale = scale;
     else if (A.scale_type == SWK_SCALE_PHASE_CYCLING) lin_pc = __fmul_rn(A.lin_pc, scale); // monte_carlo.cu:303
 
-    const int n3[3] = {(int)A.nx, (int)A.ny, (int)A.nz};
-    float inv_h[3]; // grid units per metre at scale 1
+    const uint32_t n3[3] = {A.nx, A.ny, A.nz};
+    double inv_h[3]; // grid units per metre at scale 1
 #pragma unroll
-    for (int i = 0; i < 3; i++) inv_h[i] = (float)n3[i] / A.fov[i];
+    for (int i = 0; i < 3; i++) inv_h[i] = (double)n3[i] / (double)A.fov[i];
+
+    // ---- fraction bits of this block's scale (block-uniform) ----
+    uint32_t fb;
     {
         const double *tsig = blob_ptr<double>(A.blob, L.sigma);
+        double smax = 0.;
+        for (uint32_t s = 0; s < L.n_sub; s++)
+            for (int i = 0; i < 3; i++) smax = fmax(smax, tsig[s] * inv_h[i] / (double)fscale);
+        const uint32_t nmax = max(n3[0], max(n3[1], n3[2]));
+        int f = 22;
+        while (f > 0 && ((double)(nmax + 1u) * (double)(1u << f) + 4194304. > 4294967296.)) f--; // (b)
+        while (f > 0 && 5.7 * smax * (double)(1u << f) >= 4194304.) f--;                           // (a)
+        fb = (uint32_t)f;
         for (uint32_t i = threadIdx.x; i < 3u * L.n_sub; i += kBlock) {
             const uint32_t ax = i % 3u;
-            const float ih = ax == 0 ? inv_h[0] : (ax == 1 ? inv_h[1] : inv_h[2]);
-            sgt[i] = (float)(tsig[i / 3u] * (double)ih / (double)fscale);
+            const double ih = ax == 0 ? inv_h[0] : (ax == 1 ? inv_h[1] : inv_h[2]);
+            sgt[i] = (float)(tsig[i / 3u] * ih / (double)fscale * (double)(1u << f));
         }
     }
     __syncthreads();
+    // metres per fixed-point unit at this scale (events and outputs only)
+    const double unit_m[3] = {(double)fscale / (inv_h[0] * (double)(1u << fb)), (double)fscale / (inv_h[1] * (double)(1u << fb)),
+                              (double)fscale / (inv_h[2] * (double)(1u << fb))};
 
     const int32_t  *tl_time = blob_ptr<int32_t>(B, L.tl_time);
     const uint32_t *tl_mask = blob_ptr<uint32_t>(B, L.tl_mask);
     const float *tT1 = blob_ptr<float>(B, L.T1s), *tT2 = blob_ptr<float>(B, L.T2s), *tpXY = blob_ptr<float>(B, L.pXY);
 
     // ---- which spin ----
-    const uint32_t j = (blockIdx.x / A.n_scales) * kBlock + threadIdx.x;
-    bool alive = j < A.n_local;
+    const uint32_t j = A.j_first + (blockIdx.x / A.n_scales) * kBlock + threadIdx.x;
+    bool alive = j < A.j_end;
     const uint32_t jl = alive ? (A.order ? __ldg(A.order + j) : j) : 0u;
     const uint32_t spin_no = A.spin_first + jl; // GLOBAL spin id: RNG key and dephasing term
 
     float m[3] = {0.f, 0.f, 1.f};
-    float pf[3];
-    int pv[3];
+    uint32_t p0, p1, p2; // fixed-point position
     {
-        float x0[3] = {0.f, 0.f, 0.f};
-        if (alive) {
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                x0[i] = __ldg(A.xyz0 + 3 * (size_t)jl + i);
-                if (A.m0) m[i] = __ldg(A.m0 + 3 * (size_t)jl + i);
-            }
-        }
+        uint32_t pp[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            const float g = x0[i] * inv_h[i];
-            int v = __float2int_rd(g);
-            v = max(0, min(v, n3[i] - 1));
-            pv[i] = v;
-            pf[i] = fminf(fmaxf(g - (float)v, 0.f), 0.99999994f); // spins exactly on the far wall start in the last voxel
+            float x0 = 0.f;
+            if (alive) {
+                x0 = __ldg(A.xyz0 + 3 * (size_t)jl + i);
+                if (A.m0) m[i] = __ldg(A.m0 + 3 * (size_t)jl + i);
+            }
+            double g = (double)x0 * inv_h[i] * (double)(1u << fb);
+            const double hi = (double)n3[i] * (double)(1u << fb) - 1.; // spins exactly on the far wall start in the last voxel
+            g = fmin(fmax(g, 0.), hi);
+            pp[i] = (uint32_t)g;
         }
+        p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
     }
     const uint32_t ny = A.ny, nz = A.nz;
-    uint32_t ind_cur = ((uint32_t)pv[0] * ny + (uint32_t)pv[1]) * nz + (uint32_t)pv[2];
+    uint32_t ind_cur = ((p0 >> fb) * ny + (p1 >> fb)) * nz + (p2 >> fb);
     uint32_t ts_old = alive ? (uint32_t)__ldg(A.mask + ind_cur) : 0u;
     const bool has_field = VOX != VOX_MASK;
     const float field_k = A.field_k;
@@ -183,13 +207,13 @@ __global__ void __launch_bounds__(kBlock, 4) walk_fast_kernel(const __grid_const
     float field = 0.f;
     if (alive && VOX == VOX_SPLIT) field = __fmul_rn(__ldg(A.fieldmap + ind_cur), field_k);
     if (alive && VOX == VOX_PACKED) field = __fmul_rn(__uint_as_float(__ldg(A.packed + ind_cur) & 0xfffffff0u), field_k);
-    float sg[3] = {sgt[3 * ts_old], sgt[3 * ts_old + 1], sgt[3 * ts_old + 2]};
+    float sg0 = sgt[3 * ts_old], sg1 = sgt[3 * ts_old + 1], sg2 = sgt[3 * ts_old + 2];
 
     uint32_t ctr = 0, itr = 0;
     const uint32_t seed_lo = (uint32_t)A.seed;
     const uint32_t seed_hi_walk = ((uint32_t)(A.seed >> 32) & 0x3fffffffu) | (STREAM_WALK << 30);
     const uint32_t seed_hi_perm = ((uint32_t)(A.seed >> 32) & 0x3fffffffu) | (STREAM_PERMEABILITY << 30);
-    unsigned long long st_mask = 0, st_field = 0, st_rej = 0, st_steps = 0;
+    uint32_t st_mask = 0, st_field = 0, st_rej = 0, st_steps = 0; // per thread and launch: < 2^32
     bool lost = false;
 
     const size_t out_row = (size_t)k * A.n_local + jl;
@@ -227,33 +251,37 @@ __global__ void __launch_bounds__(kBlock, 4) walk_fast_kernel(const __grid_const
 
             // =============================== inner loop ===============================
             while (rem > 0) {
-                float g0 = fmaf(n0, sg[0], pf[0]), g1 = fmaf(n1, sg[1], pf[1]), g2 = fmaf(n2, sg[2], pf[2]);
-                // fraction still in [0,1)  <=>  bit pattern below 1.0f (negative floats compare above)
-                const bool hop = (__float_as_uint(g0) >= 0x3f800000u) | (__float_as_uint(g1) >= 0x3f800000u) |
-                                 (__float_as_uint(g2) >= 0x3f800000u);
-                int v0 = pv[0], v1 = pv[1], v2 = pv[2];
-                uint32_t ind_new = ind_cur, ts = ts_old;
+                uint32_t q0 = fx_step(p0, n0, sg0), q1 = fx_step(p1, n1, sg1), q2 = fx_step(p2, n2, sg2);
+                const bool hop = (((p0 ^ q0) | (p1 ^ q1) | (p2 ^ q2)) >> fb) != 0u;
+                uint32_t ts = ts_old;
                 float fv = 0.f;
+                uint32_t ind_new = ind_cur; // STATS bookkeeping only
+                bool chg = false;
                 if (hop) {
-                    if (__float_as_uint(g0) >= 0x3f800000u) hop_axis(g0, v0, pf[0], n0 * sg[0], pv[0], n3[0], A.cross_fov);
-                    if (__float_as_uint(g1) >= 0x3f800000u) hop_axis(g1, v1, pf[1], n1 * sg[1], pv[1], n3[1], A.cross_fov);
-                    if (__float_as_uint(g2) >= 0x3f800000u) hop_axis(g2, v2, pf[2], n2 * sg[2], pv[2], n3[2], A.cross_fov);
-                    ind_new = ((uint32_t)v0 * ny + (uint32_t)v1) * nz + (uint32_t)v2;
+                    uint32_t v0 = q0 >> fb, v1 = q1 >> fb, v2 = q2 >> fb;
+                    if ((v0 >= n3[0]) | (v1 >= n3[1]) | (v2 >= n3[2])) { // FoV boundary (kernels.cu:133-136), rare
+                        if (v0 >= n3[0]) { q0 = fov_boundary(q0, p0, n3[0], fb, A.cross_fov); v0 = q0 >> fb; }
+                        if (v1 >= n3[1]) { q1 = fov_boundary(q1, p1, n3[1], fb, A.cross_fov); v1 = q1 >> fb; }
+                        if (v2 >= n3[2]) { q2 = fov_boundary(q2, p2, n3[2], fb, A.cross_fov); v2 = q2 >> fb; }
+                    }
+                    ind_new = (v0 * ny + v1) * nz + v2;
+                    if (STATS) { chg = (ind_new != ind_cur) | fresh; st_mask += chg; }
                     if (VOX == VOX_PACKED) { // one gather: consumed after the next RNG block
-                        const uint32_t w = __ldg(A.packed + ind_new);
+                        const uint32_t w = ldg_voxel(A.packed + ind_new);
                         ts = w & 15u;
                         fv = __uint_as_float(w & 0xfffffff0u);
                     } else {                 // both gathers issued back to back, consumed after the next RNG block
                         ts = __ldg(A.mask + ind_new);
                         if (VOX == VOX_SPLIT) fv = __ldg(A.fieldmap + ind_new);
                     }
+                } else if (STATS && fresh) {
+                    st_mask++; st_field++;
                 }
-                // ---- random numbers of the next attempt: independent work that overlaps the gathers ----
+                // ---- random numbers of the next attempt: independent work that overlaps the gather ----
                 const uint32_t ctr_this = ctr++;
                 normals3_fast(philox_fixed(ctr, seed_lo, spin_no, seed_hi_walk), n0, n1, n2);
 
                 if (hop) { // kernels.cu:150-170
-                    if (STATS) st_mask += (ind_new != ind_cur || fresh);
                     if (ts != ts_old) {
                         const float u = u01_open1(philox_fixed(ctr_this, seed_lo, spin_no, seed_hi_perm).x);
                         if (u >= tpXY[ts_old * L.n_sub + ts]) {
@@ -262,24 +290,19 @@ __global__ void __launch_bounds__(kBlock, 4) walk_fast_kernel(const __grid_const
                             continue; // redraw from the old position; time does not advance
                         }
                         ts_old = ts;
-                        sg[0] = sgt[3 * ts]; sg[1] = sgt[3 * ts + 1]; sg[2] = sgt[3 * ts + 2];
+                        sg0 = sgt[3 * ts]; sg1 = sgt[3 * ts + 1]; sg2 = sgt[3 * ts + 2];
                     }
-                    if (STATS) { st_field += (ind_new != ind_cur || fresh); }
-                    ind_cur = ind_new;
-                    pv[0] = v0; pv[1] = v1; pv[2] = v2;
                     if (has_field) field = __fmul_rn(fv, field_k); // monte_carlo.cu:244
-                } else if (STATS && fresh) {
-                    st_mask++; st_field++;
+                    if (STATS) { st_field += chg; ind_cur = ind_new; }
                 }
                 if (STATS) { fresh = false; st_steps++; }
-                pf[0] = g0; pf[1] = g1; pf[2] = g2;
+                p0 = q0; p1 = q1; p2 = q2;
                 acc += field; // kernels.cu:171-172
                 itr = 0;
                 if (RECORD) { // kernels.cu:218-221 (diagnostic mode)
                     if (X1) {
                         float *slot = X1 + 3 * ((size_t)scan * n_tp + (t_stop - (uint32_t)rem));
-#pragma unroll
-                        for (int i = 0; i < 3; i++) slot[i] = (float)(((double)pv[i] + (double)pf[i]) / (double)inv_h[i] * (double)fscale);
+                        slot[0] = (float)((double)p0 * unit_m[0]); slot[1] = (float)((double)p1 * unit_m[1]); slot[2] = (float)((double)p2 * unit_m[2]);
                     }
                 }
                 rem--;
@@ -300,9 +323,7 @@ __global__ void __launch_bounds__(kBlock, 4) walk_fast_kernel(const __grid_const
                 if (alive) {
                     const float Gx = __fmul_rn(blob_ptr<float>(B, L.gx)[cnt_grad], gscale), Gy = __fmul_rn(blob_ptr<float>(B, L.gy)[cnt_grad], gscale),
                                 Gz = __fmul_rn(blob_ptr<float>(B, L.gz)[cnt_grad], gscale); // monte_carlo.cu:288-290
-                    const double X = ((double)pv[0] + (double)pf[0]) / (double)inv_h[0] * (double)fscale;
-                    const double Y = ((double)pv[1] + (double)pf[1]) / (double)inv_h[1] * (double)fscale;
-                    const double Z = ((double)pv[2] + (double)pf[2]) / (double)inv_h[2] * (double)fscale;
+                    const double X = (double)p0 * unit_m[0], Y = (double)p1 * unit_m[1], Z = (double)p2 * unit_m[2];
                     double g = __fma_rn((double)Gz, Z, __fma_rn((double)Gx, X, __dmul_rn((double)Gy, Y)));
                     g = g * 1e-3 * (double)A.timestep_us * 1e-6 * kGamma;
                     acc = (float)__fma_rn(g, kRad2Deg, (double)acc);
@@ -354,9 +375,8 @@ __global__ void __launch_bounds__(kBlock, 4) walk_fast_kernel(const __grid_const
     }
 
     // ---- final position (kernels.cu:220-221 leaves the last committed position in xyz1) ----
-    if (!RECORD && X1 && j < A.n_local) {
-#pragma unroll
-        for (int i = 0; i < 3; i++) X1[i] = (float)(((double)pv[i] + (double)pf[i]) / (double)inv_h[i] * (double)fscale);
+    if (!RECORD && X1 && j < A.j_end) {
+        X1[0] = (float)((double)p0 * unit_m[0]); X1[1] = (float)((double)p1 * unit_m[1]); X1[2] = (float)((double)p2 * unit_m[2]);
     }
 
     // ---- flush block sums and counters ----
@@ -370,24 +390,23 @@ __global__ void __launch_bounds__(kBlock, 4) walk_fast_kernel(const __grid_const
     }
     if (A.counters) {
         if (STATS) {
+            unsigned long long c0 = st_steps, c1 = st_mask, c2 = st_field, c3 = st_rej;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                st_steps += __shfl_xor_sync(0xffffffffu, st_steps, o);
-                st_mask += __shfl_xor_sync(0xffffffffu, st_mask, o);
-                st_field += __shfl_xor_sync(0xffffffffu, st_field, o);
-                st_rej += __shfl_xor_sync(0xffffffffu, st_rej, o);
+                c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+                c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+            }
+            if ((threadIdx.x & 31u) == 0) {
+                atomicAdd(A.counters + 0, c0);
+                atomicAdd(A.counters + 1, c1);
+                atomicAdd(A.counters + 2, c2);
+                atomicAdd(A.counters + 3, c3);
             }
         }
         const unsigned lost_w = __popc(__ballot_sync(0xffffffffu, lost));
-        if ((threadIdx.x & 31u) == 0) {
-            if (STATS) {
-                atomicAdd(A.counters + 0, st_steps);
-                atomicAdd(A.counters + 1, st_mask);
-                atomicAdd(A.counters + 2, st_field);
-                atomicAdd(A.counters + 3, st_rej);
-            }
-            if (lost_w) atomicAdd(A.counters + 4, (unsigned long long)lost_w);
-        }
+        if ((threadIdx.x & 31u) == 0 && lost_w) atomicAdd(A.counters + 4, (unsigned long long)lost_w);
     }
 }
 

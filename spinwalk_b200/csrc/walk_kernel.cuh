@@ -74,6 +74,7 @@ struct WalkArgs {
     const float *m0;         // [n_local][3] or nullptr => (0,0,1)
     const uint32_t *order;   // nullptr, or thread j simulates local spin order[j] (locality sort)
     uint32_t spin_first, n_local;
+    uint32_t j_first, j_end; // this launch simulates thread slots [j_first, j_end) of the shard (pipelined host runs launch slices)
     // outputs (any may be nullptr), reference layouts restricted to the shard
     float   *M1;             // [K][n_local][E][3]
     float   *XYZ1;           // [K][n_local][trj][3]
@@ -274,8 +275,8 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
 
     // ---- which (spin, scale) ------------------------------------------------------------------
     const uint32_t k = blockIdx.x % A.n_scales;
-    const uint32_t j = (blockIdx.x / A.n_scales) * kBlock + threadIdx.x; // thread slot in the shard
-    bool alive = j < A.n_local;
+    const uint32_t j = A.j_first + (blockIdx.x / A.n_scales) * kBlock + threadIdx.x; // thread slot in the shard
+    bool alive = j < A.j_end;
     const uint32_t jl = alive ? (A.order ? A.order[j] : j) : 0u;          // local spin index
     const uint32_t spin_no = A.spin_first + jl;                          // GLOBAL spin id
     const float scale = __ldg(A.scales + k);
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
     }
 
     // ---- final position (kernels.cu:220-221 leaves the last committed position in xyz1) ----
-    if (!A.record && X1 && j < A.n_local) {
+    if (!A.record && X1 && j < A.j_end) {
         if (MODE == SWK_MODE_COMPAT) {
 #pragma unroll
             for (int i = 0; i < 3; i++) xyz_f[i] = (float)px[i];
