@@ -5,7 +5,9 @@
 // launches ONE kernel for all scales, and hands results back in the reference's layouts.
 // No CPU fallback exists: every entry point needs a CUDA device.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -21,6 +23,19 @@
 using namespace swk;
 
 namespace {
+
+// SWK_TRACE=1: host-side phase timings of a run on stderr (diagnostics only)
+struct Trace {
+    bool on = getenv("SWK_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what)
+    {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[swk] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 thread_local std::string g_create_error;
 
@@ -60,6 +75,7 @@ struct swk_engine {
 
     // spins
     DevBuf xyz0, m0, order;
+    DevBuf sort_keys_in, sort_keys_out, sort_ids, sort_tmp; // kept between runs: re-sorting after every swk_set_spins must not malloc
     bool order_valid = false;
     uint32_t order_slice = 0; // slice length the order was built for (0 = one slice)
     uint32_t spin_first = 0, n_local = 0;
@@ -241,7 +257,8 @@ void swk_destroy(swk_engine *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
-    for (DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters})
+    for (DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
+                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp})
         release(*b);
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -485,6 +502,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         }
     }
 
+    Trace tr;
     CK(cudaMemcpyAsync(e->scales.p, scales, K * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(cudaEventRecord(e->evA, e->stream));
     // outputs start at zero: lost spins / unwritten echoes read back as 0 (monte_carlo.cu:256,259-260)
@@ -494,13 +512,14 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     if (E * ns) CK(cudaMemsetAsync(sums, 0, K * E * ns * 4 * sizeof(double), e->stream));
     CK(cudaMemsetAsync(e->counters.p, 0, e->counters.bytes, e->stream));
 
+    tr.mark("alloc + memset enqueue");
     uint32_t extra_launches = 0;
     const uint32_t want_order_slice = n_slices > 1 ? slice_len : 0u;
     if (flags & SWK_RUN_NO_SORT) {
         release(e->order);
         e->order_valid = false;
     } else if (!e->order_valid || e->order_slice != want_order_slice) {
-        DevBuf keys_in, keys_out, ids_in, tmp;
+        DevBuf &keys_in = e->sort_keys_in, &keys_out = e->sort_keys_out, &ids_in = e->sort_ids, &tmp = e->sort_tmp;
         int rs = SWK_OK;
         size_t tmp_bytes = 0;
         if ((rs = ensure(e, e->order, S * sizeof(uint32_t))) == SWK_OK && (rs = ensure(e, keys_in, S * 8)) == SWK_OK &&
@@ -516,16 +535,15 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             if (ce == cudaSuccess && (rs = ensure(e, tmp, tmp_bytes)) == SWK_OK)
                 ce = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, static_cast<uint64_t *>(keys_in.p), static_cast<uint64_t *>(keys_out.p),
                                                      static_cast<uint32_t *>(ids_in.p), static_cast<uint32_t *>(e->order.p), (int)S, 0, 64, e->stream);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
             if (ce != cudaSuccess) rs = fail(e, SWK_ERR_CUDA, std::string("spin ordering: ") + cudaGetErrorString(ce));
         }
-        release(keys_in); release(keys_out); release(ids_in); release(tmp);
         if (rs != SWK_OK) return rs;
         e->order_valid = true;
         e->order_slice = want_order_slice;
         extra_launches++;
     }
 
+    tr.mark("spin ordering");
     // compact voxel words for the FAST walk (built once per phantom)
     const bool want_packed = mode == SWK_MODE_FAST && e->fieldmap.p && e->mask_substrates <= 16 && !(flags & SWK_RUN_NO_PACK);
     if (want_packed && !e->packed_valid) {
@@ -607,21 +625,21 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         CK(cudaGetLastError());
     } else {
         // slice i runs on compute stream i & 1 (tails overlap the next slice); its rows are downloaded as soon as it is done
+        const bool one_stream = getenv("SWK_ONE_CSTREAM") != nullptr; // tuning knob
         for (int c = 0; c < 2; c++) CK(cudaStreamWaitEvent(e->cstream[c], e->ev0, 0));
         for (uint32_t i = 0; i < n_slices; i++) {
             A.j_first = i * slice_len;
             A.j_end = (uint32_t)std::min<size_t>(S, (size_t)(i + 1) * slice_len);
             const uint64_t grid = (((uint64_t)(A.j_end - A.j_first) + kBlock - 1) / kBlock) * K;
-            kern<<<(unsigned)grid, kBlock, smem, e->cstream[i & 1]>>>(A);
+            cudaStream_t cs = e->cstream[one_stream ? 0 : (i & 1)];
+            kern<<<(unsigned)grid, kBlock, smem, cs>>>(A);
             CK(cudaGetLastError());
-            CK(cudaEventRecord(e->ev_slice[i], e->cstream[i & 1]));
+            CK(cudaEventRecord(e->ev_slice[i], cs));
         }
         CK(cudaStreamWaitEvent(e->stream, e->ev_slice[n_slices - 1], 0));
         CK(cudaStreamWaitEvent(e->stream, e->ev_slice[n_slices - 2], 0));
     }
     CK(cudaEventRecord(e->ev1, e->stream));
-    unsigned long long cnt[8] = {0};
-    CK(cudaMemcpyAsync(cnt, e->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, e->stream));
     if (host && n_slices > 1) { // rows [j_first, j_end) of every scale: one strided copy per array and slice
         for (uint32_t i = 0; i < n_slices; i++) {
             const size_t r0 = (size_t)i * slice_len, r1 = std::min<size_t>(S, r0 + slice_len);
@@ -643,8 +661,13 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             }
         }
     }
+    tr.mark("launches enqueued");
+    unsigned long long cnt[8] = {0}; // pageable destination: this copy blocks until the kernels are done, so it comes after all enqueues
+    CK(cudaMemcpyAsync(cnt, e->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream)); // ≙ the device sync after the launch (monte_carlo.cu:333)
+    tr.mark("kernels done");
     if (host && n_slices > 1) CK(cudaStreamSynchronize(e->dstream));
+    tr.mark("downloads done");
     float ms = 0.f, ms_all = 0.f;
     CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     CK(cudaEventElapsedTime(&ms_all, e->evA, e->ev1));
@@ -710,10 +733,14 @@ int swk_run(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_fir
 {
     if (!e) return SWK_ERR_INVALID;
     int rc;
+    Trace tr;
     if ((rc = swk_set_spins(e, XYZ0, M0, spin_first, n_local)) != SWK_OK) return rc;
+    tr.mark("set_spins (H2D)");
     const int flags = (M1 ? SWK_OUT_M1 : 0) | (XYZ1 ? SWK_OUT_XYZ1 : 0) | (T ? SWK_OUT_T : 0) | (stats ? SWK_RUN_STATS : 0);
-    // Large runs are cut into slices of >= 2^18 spins so that the device-to-host copy of slice i overlaps the walk of slice i+1.
-    const uint32_t n_slices = (M1 || XYZ1 || T) ? std::min<uint32_t>(16u, std::max<uint32_t>(1u, n_local >> 18)) : 1u;
+    // Large runs are cut into <= 8 slices of >= 2^21 spins so that the device-to-host copy of slice i overlaps the walk of slice
+    // i+1 (measured on C2: 4 slices cost 0.5 % each in kernel time and leave 1/4 of the 0.24 s download exposed).
+    uint32_t n_slices = (M1 || XYZ1 || T) ? std::min<uint32_t>(8u, std::max<uint32_t>(1u, n_local >> 21)) : 1u;
+    if (const char *ev = getenv("SWK_SLICES")) n_slices = std::max(1, atoi(ev)); // tuning knob
     HostOut host;
     host.M1 = M1; host.XYZ1 = XYZ1; host.T = T;
     if ((rc = run_impl(e, scales, n_scales, scale_type, mode, flags, nullptr, n_slices, &host)) != SWK_OK) return rc;
@@ -729,7 +756,8 @@ uint64_t swk_device_bytes(const swk_engine *e)
 {
     if (!e) return 0;
     uint64_t n = 0;
-    for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters})
+    for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
+                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp})
         n += b->bytes;
     return n;
 }

@@ -95,10 +95,11 @@ __device__ __noinline__ uint32_t fov_boundary(uint32_t q, const uint32_t p, cons
 }
 
 // The voxel gather.  A plain ld.global.nc makes L2 fetch the whole 128 B line from HBM (measured: 3.7 sectors per
-// missed sector, tools/gather_probe.cu); the L2::64B prefetch-size qualifier halves that traffic at the same gather rate.
+// missed sector, tools/gather_probe.cu); the L2::64B prefetch-size qualifier (LDG.E.LTC64B) halves that traffic at the
+// same gather rate — the rate is bound by HBM row activations, not bytes — and keeps the board under its power cap.
 __device__ __forceinline__ uint32_t ldg_voxel(const uint32_t *p)
 {
-#ifdef SWK_GATHER_L2_64B
+#ifndef SWK_GATHER_L2_128B
     uint32_t v;
     asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;

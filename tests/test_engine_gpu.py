@@ -172,10 +172,11 @@ def test_device_resident_run_and_device_positions(sw):
         assert np.isfinite(x1).all() and (x1 >= 0).all() and (x1 < np.asarray(fov)).all()
 
 
-def test_pipelined_host_run_equals_single_launch(sw):
-    """swk_run cuts runs of >= 2^19 spins into slices (two compute streams, download of slice i overlapping the walk of
-    slice i+1) and sorts spins slice-major; results are keyed by spin id, so they must equal the single-launch
-    run_device + download bit for bit, and the ensemble sums must agree."""
+def test_pipelined_host_run_equals_single_launch(sw, monkeypatch):
+    """swk_run cuts large runs into slices (two compute streams, download of slice i overlapping the walk of slice i+1)
+    and sorts spins slice-major; results are keyed by spin id, so they must equal the single-launch
+    run_device + download bit for bit, and the ensemble sums must agree.  SWK_SLICES forces 3 slices at a test-sized run."""
+    monkeypatch.setenv("SWK_SLICES", "3")
     case, mask, fm, fov, _ = cases.gre(n_spins=3 * 2**18 + 777, scales=(0.3, 2.0))
     case.TR_us, case.TE_tp = 2500, [20, 45]
     rng = np.random.default_rng(4)
