@@ -576,6 +576,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     A.max_iter = e->P.max_iterations;
     A.cross_fov = e->P.cross_fov;
     A.record = e->P.record_trajectory;
+    A.one_bits = 0x3f800000u;
     A.blob = static_cast<const uint8_t *>(e->blob.p);
     A.L = e->L;
     A.scales = static_cast<const float *>(e->scales.p);

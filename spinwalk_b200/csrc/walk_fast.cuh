@@ -67,6 +67,33 @@ __device__ __forceinline__ void normals3_fast(const uint4 r, float &n0, float &n
     n2 = rb * mufu_cos(tb);
 }
 
+// six N(0,1) from ONE 128-bit Philox block: three Box-Muller pairs.  Pair i takes its radius uniform from the top 23 bits
+// of word i (r.x / r.y / r.z) and its 19-bit angle uniform from the remaining 9 bits of that word followed by a 10-bit field
+// of r.w — 126 of the 128 bits, no bit used twice.  |n| <= sqrt(2 ln 2^23) = 5.65.  One block feeds TWO attempts of the walk.
+//   `one` holds 0x3f800000 in a REGISTER (it arrives as a kernel argument so that ptxas cannot turn it back into an
+//   immediate): (x & 0x007ffff0) | one is then a single LOP3 instead of two.
+__device__ __forceinline__ uint32_t and_or(const uint32_t x, const uint32_t one)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, 0x007ffff0, %2, 0xEA;" : "=r"(d) : "r"(x), "r"(one)); // (x & imm) | one
+    return d;
+}
+__device__ __forceinline__ void bm_pair(const uint32_t w, const uint32_t wlo, const uint32_t one, float &a, float &b)
+{
+    const float kNeg2Ln2 = -1.3862943611198906f, k2Pi = 6.283185307179586f;
+    const float u = 2.0f - __uint_as_float((w >> 9) + 0x3f800000u);                       // (0,1], 23 bits: w[31:9]   (LEA.HI)
+    const float t = __uint_as_float(and_or(__funnelshift_l(wlo, w, 14), one)) * k2Pi;     // [2 pi, 4 pi): w[8:0] ++ wlo[31:22]
+    const float r = mufu_sqrt(kNeg2Ln2 * mufu_lg2(u));
+    a = r * mufu_cos(t);
+    b = r * mufu_sin(t);
+}
+__device__ __forceinline__ void normals6_fast(const uint4 r, const uint32_t one, float &a0, float &a1, float &a2, float &b0, float &b1, float &b2)
+{
+    bm_pair(r.x, r.w, one, a0, a1);       // angle bits: r.x[8:0] ++ r.w[31:22]
+    bm_pair(r.y, r.w << 10, one, a2, b0); //             r.y[8:0] ++ r.w[21:12]
+    bm_pair(r.z, r.w << 20, one, b1, b2); //             r.z[8:0] ++ r.w[11:2]
+}
+
 // ---- fixed-point grid coordinates -------------------------------------------------------------------------------
 // pos = voxel << FB | fraction, FB chosen per launch-block (per scale) on the host side of the kernel:
 //   (a) 5.65 sigma_vox 2^FB < 2^22   so that the magic-number rounding of the step is exact to one unit,
@@ -97,15 +124,13 @@ __device__ __noinline__ uint32_t fov_boundary(uint32_t q, const uint32_t p, cons
 // The voxel gather.  A plain ld.global.nc makes L2 fetch the whole 128 B line from HBM (measured: 3.7 sectors per
 // missed sector, tools/gather_probe.cu); the L2::64B prefetch-size qualifier (LDG.E.LTC64B) halves that traffic at the
 // same gather rate — the rate is bound by HBM row activations, not bytes — and keeps the board under its power cap.
+// (An L2 evict_first policy for the blocks of the small FoV scales, which touch the whole table at random, was measured
+// on C2 and made the pass 2-7 % slower at every threshold; the gather therefore carries no eviction hint.)
 __device__ __forceinline__ uint32_t ldg_voxel(const uint32_t *p)
 {
-#ifndef SWK_GATHER_L2_128B
     uint32_t v;
     asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
-#else
-    return __ldg(p);
-#endif
 }
 
 // VOX selects how a voxel is fetched: 0 = mask only (no fieldmap), 1 = mask byte + FP32 field (two gathers issued
@@ -210,7 +235,7 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
     if (alive && VOX == VOX_PACKED) field = __fmul_rn(__uint_as_float(__ldg(A.packed + ind_cur) & 0xfffffff0u), field_k);
     float sg0 = sgt[3 * ts_old], sg1 = sgt[3 * ts_old + 1], sg2 = sgt[3 * ts_old + 2];
 
-    uint32_t ctr = 0, itr = 0;
+    uint32_t itr = 0;
     const uint32_t seed_lo = (uint32_t)A.seed;
     const uint32_t seed_hi_walk = ((uint32_t)(A.seed >> 32) & 0x3fffffffu) | (STREAM_WALK << 30);
     const uint32_t seed_hi_perm = ((uint32_t)(A.seed >> 32) & 0x3fffffffu) | (STREAM_PERMEABILITY << 30);
@@ -227,8 +252,11 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
     }
 
     const uint32_t n_tp = A.n_tp;
-    float n0, n1, n2; // normals of the NEXT attempt
-    normals3_fast(philox_fixed(ctr, seed_lo, spin_no, seed_hi_walk), n0, n1, n2);
+    // One Philox block feeds TWO attempts: the even attempt of block `blk` steps by (na*), the odd one by (nb*).
+    uint32_t blk = 0;
+    const uint32_t kOne = A.one_bits; // 0x3f800000, deliberately opaque to ptxas (see and_or)
+    float na0, na1, na2, nb0, nb1, nb2;
+    normals6_fast(philox_fixed(blk, seed_lo, spin_no, seed_hi_walk), kOne, na0, na1, na2, nb0, nb1, nb2);
 
     for (uint32_t scan = 0; scan < A.n_scans; scan++) {
         const bool last_scan = (scan + 1 == A.n_scans);
@@ -251,8 +279,10 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
             int rem = alive ? (int)(t_stop - t) : 0; // accepted steps still to take before the next event
 
             // =============================== inner loop ===============================
-            while (rem > 0) {
-                uint32_t q0 = fx_step(p0, n0, sg0), q1 = fx_step(p1, n1, sg1), q2 = fx_step(p2, n2, sg2);
+            // one attempt = one tentative step (kernels.cu:130-170).  `overlap` is independent work (random numbers of later
+            // attempts) placed between ISSUING the voxel gather and CONSUMING it.  Returns true when the step was accepted.
+            auto attempt = [&](const float a0, const float a1, const float a2, const uint32_t perm_ctr, auto &&overlap) -> bool {
+                uint32_t q0 = fx_step(p0, a0, sg0), q1 = fx_step(p1, a1, sg1), q2 = fx_step(p2, a2, sg2);
                 const bool hop = (((p0 ^ q0) | (p1 ^ q1) | (p2 ^ q2)) >> fb) != 0u;
                 uint32_t ts = ts_old;
                 float fv = 0.f;
@@ -267,28 +297,29 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
                     }
                     ind_new = (v0 * ny + v1) * nz + v2;
                     if (STATS) { chg = (ind_new != ind_cur) | fresh; st_mask += chg; }
-                    if (VOX == VOX_PACKED) { // one gather: consumed after the next RNG block
+                    if (VOX == VOX_PACKED) { // one gather
                         const uint32_t w = ldg_voxel(A.packed + ind_new);
                         ts = w & 15u;
                         fv = __uint_as_float(w & 0xfffffff0u);
-                    } else {                 // both gathers issued back to back, consumed after the next RNG block
+                    } else {                 // both gathers issued back to back
                         ts = __ldg(A.mask + ind_new);
                         if (VOX == VOX_SPLIT) fv = __ldg(A.fieldmap + ind_new);
                     }
                 } else if (STATS && fresh) {
                     st_mask++; st_field++;
                 }
-                // ---- random numbers of the next attempt: independent work that overlaps the gather ----
-                const uint32_t ctr_this = ctr++;
-                normals3_fast(philox_fixed(ctr, seed_lo, spin_no, seed_hi_walk), n0, n1, n2);
-
+                overlap();
                 if (hop) { // kernels.cu:150-170
                     if (ts != ts_old) {
-                        const float u = u01_open1(philox_fixed(ctr_this, seed_lo, spin_no, seed_hi_perm).x);
-                        if (u >= tpXY[ts_old * L.n_sub + ts]) {
+                        // accept iff u < P_XY[from][to], u in [0,1) (kernels.cu:154).  P <= 0 always rejects and P >= 1 always accepts:
+                        // the uniform (its own Philox stream, so skipping a draw changes nothing else) is only generated in between.
+                        const float pxy = tpXY[ts_old * L.n_sub + ts];
+                        bool reject = pxy <= 0.f;
+                        if (pxy > 0.f && pxy < 1.f) reject = u01_open1(philox_fixed(perm_ctr, seed_lo, spin_no, seed_hi_perm).x) >= pxy;
+                        if (reject) {
                             if (STATS) st_rej++;
-                            if (itr++ > A.max_iter) { alive = false; lost = true; break; }
-                            continue; // redraw from the old position; time does not advance
+                            if (itr++ > A.max_iter) { alive = false; lost = true; rem = 0; }
+                            return false; // redraw from the old position; time does not advance
                         }
                         ts_old = ts;
                         sg0 = sgt[3 * ts]; sg1 = sgt[3 * ts + 1]; sg2 = sgt[3 * ts + 2];
@@ -306,7 +337,20 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
                         slot[0] = (float)((double)p0 * unit_m[0]); slot[1] = (float)((double)p1 * unit_m[1]); slot[2] = (float)((double)p2 * unit_m[2]);
                     }
                 }
-                rem--;
+                return true;
+            };
+            // The integer half of the next block (Philox rounds) overlaps the gather of the even attempt, the float half
+            // (Box-Muller) that of the odd attempt.  A segment always starts on a fresh block (lanes of a warp stay in phase).
+            while (rem > 0) {
+                uint4 raw;
+                if (attempt(na0, na1, na2, 2u * blk, [&] { raw = philox_fixed(blk + 1u, seed_lo, spin_no, seed_hi_walk); })) rem--;
+                if (rem <= 0) { // the segment ends on an even attempt: (nb*) of this block are dropped
+                    normals6_fast(raw, kOne, na0, na1, na2, nb0, nb1, nb2);
+                    blk++;
+                    break;
+                }
+                if (attempt(nb0, nb1, nb2, 2u * blk + 1u, [&] { normals6_fast(raw, kOne, na0, na1, na2, nb0, nb1, nb2); })) rem--;
+                blk++;
             }
             t = t_stop - (uint32_t)rem;
             // ============================ end of inner loop ============================

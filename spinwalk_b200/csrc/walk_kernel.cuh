@@ -61,6 +61,7 @@ struct WalkArgs {
     uint32_t n_tp, n_scans, n_spins_global, n_te;
     uint64_t seed, max_iter;
     int32_t  cross_fov, record;
+    uint32_t one_bits;       // 0x3f800000 (FAST mode: a constant the compiler must keep in a register, walk_fast.cuh and_or)
     // sequence tables
     const uint8_t *blob;
     BlobLayout L;
