@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — spin-steps/s of the `sim` hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c3r|c4]
 
 A "step" is one pass of the hot path over the whole workload: all spins x all scales x all
 timepoints of one phantom (what one iteration of the reference's phantom loop does,
@@ -54,6 +54,16 @@ def workload(name: str, n_spins: int | None, n_scales: int | None):
                    linear_phase_cycling=180.0, scales=[1.0])
         ph = dict(kind="cylinder", n=600, fov_um=600.0, radius_um=8.0, bvf=4.0, Y=0.78, seed=0)
         S, desc = 10_000_000, "C4 bSSFP (config/ssfp.ini), 1101 TRs x 200 steps, 600^3 cylinder phantom, 1e7 spins, 1 scale"
+    elif name in ("c3", "c3r"):
+        from spinwalk_b200.sequences import pgse
+
+        seq = pgse([100.0 * i for i in range(1, 51)] + [0.0], (1.0, 0.0, 0.0), start_ms=15, delta_ms=10, DELTA_ms=20, timestep_us=50)
+        restricted = name == "c3r"
+        cfg = dict(base, TR_us=60050, TE_us=[60000], T1_ms=[9999999.0, 9999999.0], T2_ms=[9999999.0, 9999999.0],
+                   pXY=[1.0, 0.05, 0.05, 1.0] if restricted else [1.0, 1.0, 1.0, 1.0], cross_fov=1, **seq)
+        ph = dict(kind="spheres", n=400, fov_um=400.0, cell_um=40.0, vf=40.0, seed=0)
+        S, desc = 10_000_000, ("C3 PGSE (dwi -b 100..5000,0 -v 1 0 0 -d 15 10 20), 400^3 sphere phantom (r <= 20 um, 38 %), no fieldmap, "
+                               + ("P_XY = 0.05 (restricted)" if restricted else "P_XY = 1 (free diffusion)") + ", 1e7 spins, 51 gradient scales")
     else:
         raise SystemExit(f"unknown workload {name}")
     if n_spins:
@@ -65,9 +75,22 @@ def workload(name: str, n_spins: int | None, n_scales: int | None):
 
 
 def make_phantom_2d(ph):
-    from spinwalk_b200.phantoms import cylinder_phantom
+    """cylinders: one (x, y) plane (the phantom is invariant along z, phantom_cylinder.cpp:183-275); spheres: the 3-D mask."""
+    from spinwalk_b200.phantoms import cylinder_phantom, sphere_lattice_phantom
 
+    if ph["kind"] == "spheres":
+        return sphere_lattice_phantom(ph["n"], ph["fov_um"], ph["cell_um"], ph["vf"], ph["seed"])
     return cylinder_phantom(ph["n"], ph["fov_um"], radius_um=ph["radius_um"], bvf_pct=ph["bvf"], Y=ph["Y"], seed=ph["seed"], planar=True)
+
+
+def full_phantom(ph, mask2, fm2):
+    """host arrays [n, n, n] of the whole phantom (CPU baseline legs)."""
+    n = ph["n"]
+    if mask2.ndim == 3:
+        return mask2, fm2
+    mask = np.ascontiguousarray(np.broadcast_to(mask2[:, :, None], (n, n, n)))
+    fm = None if fm2 is None else np.ascontiguousarray(np.broadcast_to(fm2[:, :, None], (n, n, n)))
+    return mask, fm
 
 
 def make_positions(S, fov, seed, first=0):
@@ -134,8 +157,7 @@ def cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0, threads=None):
     from oracle import pyoracle as po
 
     n, nz = ph["n"], ph["n"]
-    mask = np.ascontiguousarray(np.broadcast_to(mask2[:, :, None], (n, n, nz)))
-    fm = np.ascontiguousarray(np.broadcast_to(fm2[:, :, None], (n, n, nz)))
+    mask, fm = full_phantom(ph, mask2, fm2)
     threads = threads or os.cpu_count() or 1
     kind = "reference" if po.have_ref_cpu() else "port"
     if kind == "port":
@@ -146,6 +168,8 @@ def cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0, threads=None):
                     seed=cfg_kw["seed"], B0=cfg_kw["B0"], TE_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["TE_us"]],
                     RF_FA_deg=cfg_kw["RF_FA_deg"], RF_PH_deg=cfg_kw["RF_PH_deg"], RF_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["RF_T_us"]],
                     n_dummy_scan=cfg_kw.get("n_dummy_scan", 0), linear_phase_cycling=cfg_kw.get("linear_phase_cycling", 0.0),
+                    gradient_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw.get("gradient_T_us", [])],
+                    gradX_mTm=cfg_kw.get("gradient_X_mTm", []), gradY_mTm=cfg_kw.get("gradient_Y_mTm", []), gradZ_mTm=cfg_kw.get("gradient_Z_mTm", []),
                     diffusivity=cfg_kw["diffusivity"], T1_ms=cfg_kw["T1_ms"], T2_ms=cfg_kw["T2_ms"], pXY=cfg_kw["pXY"],
                     scales=scales, scale_type=cfg_kw["scale_type"], cross_fov=cfg_kw["cross_fov"], max_iterations=cfg_kw["max_iterations"])
         x0 = make_positions(n_spins, fov, cfg_kw["seed"])
@@ -159,6 +183,9 @@ def cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0, threads=None):
     per_spin = len(scales) * (steps / (max(threads * 8, 256) * min(5, len(scales))))
     n_spins = int(max(threads * 8, min(cfg_kw["n_spins"], rate * target_s / per_spin)))
     steps, sec = run(n_spins, scales)
+    if sec < 0.5 * target_s and n_spins < cfg_kw["n_spins"]:  # the short calibration under-estimates the rate (thread start-up): size once more
+        n_spins = int(min(cfg_kw["n_spins"], n_spins * target_s / max(sec, 1e-3)))
+        steps, sec = run(n_spins, scales)
     return {"value": steps / sec, "unit": "spin-steps/s", "cores": threads, "kind": kind,
             "sample": f"first {n_spins} spins x all {len(scales)} scales of the workload ({steps:.3g} spin-steps, {sec:.1f} s); "
                       f"low spin ids keep mt19937::discard(seed+spin) cheap, which flatters the CPU reference (SURVEY App. B-3)"}, steps, sec
@@ -228,8 +255,12 @@ def main():
     cfg = sw.SimConfig(**cfg_kw_global)
     mask2, fm2, fov = make_phantom_2d(ph)
     n = ph["n"]
-    mask_d = torch.from_numpy(mask2).to(dev)[:, :, None].expand(n, n, n).contiguous()
-    fm_d = torch.from_numpy(fm2).to(dev)[:, :, None].expand(n, n, n).contiguous()
+    if mask2.ndim == 3:
+        mask_d = torch.from_numpy(mask2).to(dev)
+        fm_d = None if fm2 is None else torch.from_numpy(fm2).to(dev)
+    else:
+        mask_d = torch.from_numpy(mask2).to(dev)[:, :, None].expand(n, n, n).contiguous()
+        fm_d = torch.from_numpy(fm2).to(dev)[:, :, None].expand(n, n, n).contiguous()
 
     spin_first, n_local = sharding.shard_range(S_per_gpu * world, rank, world)  # weak scaling: S_per_gpu spins on every rank
     assert n_local == S_per_gpu
@@ -306,14 +337,36 @@ def main():
                "api": "swk_run (C-ABI) with pinned host buffers: XYZ0 in; M1, XYZ1, T, sums out"}
         del out, out_np
 
+    # ---- the voxel fetch's own roofline, measured live on this device and this phantom (untimed diagnostic launch)
+    try:
+        probe = eng.probe_gather(threads_per_sm=2048, iters=2048)
+    except Exception as ex:  # a diagnostic must never cost the bench line
+        probe = {"gathers_per_s": None, "table_bytes": None, "error": str(ex)}
+
     # ---- roofline of the walk kernel: algorithmic bytes / mean launch duration
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of this very workload from the committed ncu capture (profiles/traffic.json)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(f"{args.workload}:{args.mode}")
+        if ent and not args.spins and not args.scales:
+            traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+    except Exception:
+        pass
     per_pass_bytes = (st_counts["mask_gathers"] * 1 + st_counts["field_gathers"] * 4
                       + S_per_gpu * K * (24 + 13 * E + 12))
     ker_ms_per_launch = ker_ms / args.steps
     achieved = per_pass_bytes / (ker_ms_per_launch * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "swk::walk_kernel<FAST>" if mode == sw.MODE_FAST else "swk::walk_kernel<COMPAT>",
+    fetches_per_s = st_counts["mask_gathers"] / (ker_ms_per_launch * 1e-3)
+    gather = {"voxel_fetches_per_s": fetches_per_s, "random_gather_peak_per_s": probe.get("gathers_per_s"),
+              "frac_of_random_gather_peak": (fetches_per_s / probe["gathers_per_s"]) if probe.get("gathers_per_s") else None,
+              "table_bytes": probe.get("table_bytes"),
+              "hbm_64B_fetches_per_s": (traffic / 64 / (ker_ms_per_launch * 1e-3)) if traffic else None,
+              "note": "random_gather_peak = swk_probe_gather: dependent random 4-byte gathers over the same voxel table, nothing else "
+                      "(HBM row-activation bound, DESIGN.md §5); voxel_fetches include L1/L2 hits of the larger FoV scales"}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "gather": gather,
+                "peak_source": peak_src, "kernel": "swk::walk_fast_kernel" if mode == sw.MODE_FAST else "swk::walk_kernel<COMPAT>",
                 "algorithmic_bytes_per_launch": per_pass_bytes, "kernel_ms_per_launch": ker_ms_per_launch,
                 "bytes_per_spin_step": per_pass_bytes / steps_per_pass_rank,
                 "p_voxel_change": st_counts["mask_gathers"] / max(1, st_counts["steps"]),
@@ -326,8 +379,8 @@ def main():
             "dtype": "f32" if mode == sw.MODE_FAST else "f32+f64", "data": "synthetic",
             "config": {"workload": desc, "spins_per_gpu": S_per_gpu, "n_scales": K, "timepoints": cfg.n_timepoints,
                        "scans": eng.n_dummy_scan + 1, "spin_steps_per_pass": steps_per_pass_rank * world,
-                       "rng": "philox4x32-10 + Box-Muller (SWK_MODE_FAST)" if mode == sw.MODE_FAST else "minstd_rand + erfcinvf (SWK_MODE_COMPAT, reference arithmetic)",
-                       "l2": "inputs larger than L2 (phantom 1.08 GB vs 126 MB)" if ph["n"] >= 400 else "phantom fits in L2; outputs (>L2) rewritten every pass",
+                       "rng": "philox4x32-10, one block per two steps + Box-Muller (SWK_MODE_FAST)" if mode == sw.MODE_FAST else "minstd_rand + erfcinvf (SWK_MODE_COMPAT, reference arithmetic)",
+                       "l2": "inputs larger than L2 (phantom 1.08 GB vs 126 MB)" if ph["n"] >= 600 else "phantom fits in L2; outputs (12.5 GB > L2) rewritten every pass",
                        "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums"},
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": args.steps * st["n_launches"],
             "e2e": e2e, "roofline": roofline, "lost_spins": st_counts["lost"]}

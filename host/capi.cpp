@@ -31,3 +31,65 @@ int swkh_config_json(const char *path, int check_files, char *buf, size_t n)
 }
 
 } // extern "C"
+
+#include "h5lite.h"
+
+namespace {
+thread_local std::string g_h5_error;
+int copy_out(const std::string &s, char *buf, size_t n)
+{
+    if (s.size() + 1 > n) return -1;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return 0;
+}
+} // namespace
+
+extern "C" {
+
+const char *swkh_h5_error(void) { return g_h5_error.c_str(); }
+
+// names of the root group's links, '\n'-separated
+int swkh_h5_names(const char *path, char *buf, size_t n)
+{
+    swk_host::h5::Reader r;
+    if (!r.open(path)) { g_h5_error = r.error(); return 1; }
+    std::string s;
+    for (const auto &nm : r.names()) s += nm + "\n";
+    return copy_out(s, buf, n);
+}
+
+// dtype codes = swk_host::h5::DType order: u8 i8 u16 i16 u32 i32 u64 i64 f32 f64
+int swkh_h5_info(const char *path, const char *name, int *rank, uint64_t *dims /*[8]*/, int *dtype, int *layout)
+{
+    swk_host::h5::Reader r;
+    swk_host::h5::DatasetInfo di;
+    if (!r.open(path) || !r.info(name, di)) { g_h5_error = r.error(); return 1; }
+    if (di.dims.size() > 8) { g_h5_error = "rank > 8"; return 1; }
+    *rank = (int)di.dims.size();
+    for (size_t i = 0; i < di.dims.size(); i++) dims[i] = di.dims[i];
+    *dtype = (int)di.dtype;
+    if (layout) *layout = di.layout;
+    return 0;
+}
+
+int swkh_h5_read(const char *path, const char *name, int as_dtype, void *dst, uint64_t n_elems)
+{
+    swk_host::h5::Reader r;
+    if (!r.open(path) || !r.read(name, (swk_host::h5::DType)as_dtype, dst, n_elems)) { g_h5_error = r.error(); return 1; }
+    return 0;
+}
+
+int swkh_h5_write(const char *path, int n, const char *const *names, const int *ranks, const uint64_t *dims_flat, const int *dtypes, const void *const *data)
+{
+    swk_host::h5::Writer w(path);
+    size_t q = 0;
+    for (int i = 0; i < n; i++) {
+        std::vector<uint64_t> d(dims_flat + q, dims_flat + q + ranks[i]);
+        q += ranks[i];
+        w.add(names[i], d, (swk_host::h5::DType)dtypes[i], data[i]);
+    }
+    if (!w.close()) { g_h5_error = w.error(); return 1; }
+    return 0;
+}
+
+} // extern "C"

@@ -158,6 +158,14 @@ int swk_run(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_fir
             const float *scales, uint32_t n_scales, int scale_type, int mode,
             float *M1, float *XYZ1, uint8_t *T, double *sums, swk_stats *stats);
 
+/* ---- diagnostics: the roofline of the voxel fetch, measured on THIS device and THIS phantom ----
+ * Launches a kernel that does nothing but dependent 4-byte gathers at uniformly random addresses of the engine's voxel
+ * table (the packed words when they exist, else the fieldmap, else the mask read as words) with the walk's load
+ * instruction, `threads_per_sm` resident threads per SM and `iters` gathers per thread, and reports gathers/s
+ * (CUDA events on the engine stream).  What the walk can reach at small FoV scales, where every step lands in a
+ * voxel far from the last one.  Not part of the reference (it has no profiling hooks). */
+int swk_probe_gather(swk_engine *e, uint32_t threads_per_sm, uint32_t iters, double *gathers_per_s, uint64_t *table_bytes);
+
 /* ---- plumbing for callers that share the device with the engine (PyTorch, NCCL) ---- */
 void    *swk_stream(swk_engine *e);            /* cudaStream_t the engine launches on                       */
 double  *swk_device_sums(swk_engine *e);       /* engine-owned device sums buffer of the last run, or NULL  */

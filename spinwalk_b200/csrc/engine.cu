@@ -191,6 +191,24 @@ __global__ void sort_keys_kernel(const float *xyz0, uint32_t n, const uint8_t *m
     ids[j] = j;
 }
 
+// swk_probe_gather: dependent random gathers, no other work (same load instruction as the FAST walk).
+__device__ __forceinline__ uint32_t probe_hash(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__global__ void __launch_bounds__(256) gather_probe_kernel(const uint32_t *tab, uint32_t n_words, uint32_t iters, uint32_t *sink)
+{
+    uint32_t s = probe_hash((blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u), acc = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+        s = probe_hash(s + 0x9e3779b9u);
+        const uint32_t v = ldg_voxel(tab + (uint32_t)(((uint64_t)s * n_words) >> 32));
+        acc += v;
+        s ^= (v & 1u); // the next address waits for this gather, like the walk's permeability test
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
 bool ascending(const int32_t *t, uint32_t n)
 {
     for (uint32_t i = 1; i < n; i++)
@@ -748,6 +766,32 @@ int swk_run(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_fir
     if (e->last_slices == 1 && (rc = swk_download(e, M1, XYZ1, T)) != SWK_OK) return rc; // small runs: plain download
     if (sums && (rc = swk_get_sums(e, sums)) != SWK_OK) return rc;
     if (stats) *stats = e->stats;
+    return SWK_OK;
+}
+
+int swk_probe_gather(swk_engine *e, uint32_t threads_per_sm, uint32_t iters, double *gathers_per_s, uint64_t *table_bytes)
+{
+    if (!e || !gathers_per_s) return SWK_ERR_INVALID;
+    if (!e->has_phantom) return fail(e, SWK_ERR_STATE, "swk_probe_gather: no phantom (swk_set_phantom)");
+    if (iters == 0 || threads_per_sm == 0) return fail(e, SWK_ERR_INVALID, "swk_probe_gather: iters and threads_per_sm must be positive");
+    CK(cudaSetDevice(e->device));
+    const DevBuf &t = (e->packed_valid && e->packed.p) ? e->packed : (e->fieldmap.p ? e->fieldmap : e->mask);
+    const uint32_t n_words = (uint32_t)std::min<size_t>(t.bytes / 4, 0xffffffffu);
+    if (n_words == 0) return fail(e, SWK_ERR_STATE, "swk_probe_gather: voxel table is empty");
+    int rc;
+    if ((rc = ensure(e, e->counters, 8 * sizeof(unsigned long long))) != SWK_OK) return rc;
+    const unsigned grid = (unsigned)e->sm_count * std::max(1u, (threads_per_sm + 255u) / 256u);
+    uint32_t *sink = static_cast<uint32_t *>(e->counters.p);
+    gather_probe_kernel<<<grid, 256, 0, e->stream>>>(static_cast<const uint32_t *>(t.p), n_words, std::max(1u, iters / 8), sink); // warm-up
+    CK(cudaEventRecord(e->ev0, e->stream));
+    gather_probe_kernel<<<grid, 256, 0, e->stream>>>(static_cast<const uint32_t *>(t.p), n_words, iters, sink);
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    *gathers_per_s = (double)grid * 256.0 * iters / (ms * 1e-3);
+    if (table_bytes) *table_bytes = (uint64_t)n_words * 4;
     return SWK_OK;
 }
 

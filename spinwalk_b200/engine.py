@@ -248,6 +248,13 @@ class Engine:
         self.flags = (OUT_ALL if m1 is not None else 0)
         return dict(M1=m1, XYZ1=x1, T=t, sums=sums, stats=s.asdict() if stats else self.stats())
 
+    # ---- diagnostics ---------------------------------------------------------------------
+    def probe_gather(self, threads_per_sm=2048, iters=2048):
+        """swk_probe_gather: random dependent 4-byte gathers per second over this engine's voxel table."""
+        r, b = C.c_double(0.0), C.c_uint64(0)
+        self._ck(self._lib.swk_probe_gather(self._h, int(threads_per_sm), int(iters), C.byref(r), C.byref(b)))
+        return {"gathers_per_s": r.value, "table_bytes": b.value}
+
     # ---- plumbing ------------------------------------------------------------------------
     @property
     def stream_ptr(self):
