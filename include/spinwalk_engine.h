@@ -158,6 +158,17 @@ int swk_run(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_fir
             const float *scales, uint32_t n_scales, int scale_type, int mode,
             float *M1, float *XYZ1, uint8_t *T, double *sums, swk_stats *stats);
 
+/* ---- several engines filling ONE set of host arrays (one engine per GPU, spins sharded) ----
+ * By default swk_download / swk_run treat the host arrays as this engine's own [n_scales][n_local][...] block.  After
+ * swk_set_host_rows(e, n_rows_total, row_first) they are the GLOBAL arrays [n_scales][n_rows_total][...] of the reference
+ * (monte_carlo.cu:61-70) and this engine writes rows [row_first, row_first + n_local) of every scale — each GPU copies its
+ * contiguous slices straight into place, no exchange between GPUs.  n_rows_total = 0 restores the default. */
+int swk_set_host_rows(swk_engine *e, uint64_t n_rows_total, uint64_t row_first);
+
+/* ---- page-locked host memory for the caller's big arrays (optional; pageable buffers work, just slower) ---- */
+int  swk_alloc_pinned(void **ptr, size_t bytes);
+void swk_free_pinned(void *ptr);
+
 /* ---- diagnostics: the roofline of the voxel fetch, measured on THIS device and THIS phantom ----
  * Launches a kernel that does nothing but dependent 4-byte gathers at uniformly random addresses of the engine's voxel
  * table (the packed words when they exist, else the fieldmap, else the mask read as words) with the walk's load

@@ -64,6 +64,9 @@ SYMBOLS = {
     "swk_get_sums": (C.c_int, [_P, _P]),
     "swk_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "swk_run": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.c_int, C.c_int, _P, _P, _P, _P, C.POINTER(Stats)]),
+    "swk_set_host_rows": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
+    "swk_alloc_pinned": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "swk_free_pinned": (None, [_P]),
     "swk_probe_gather": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "swk_stream": (_P, [_P]),
     "swk_device_sums": (_P, [_P]),

@@ -84,6 +84,7 @@ struct swk_engine {
     // run state / outputs
     DevBuf scales, M1, XYZ1, T, sums, counters;
     uint32_t n_scales = 0, n_te = 0, last_slices = 1;
+    uint64_t host_rows = 0, host_row_first = 0; // swk_set_host_rows: host arrays are [K][host_rows][...], ours start at row host_row_first
     uint64_t trj = 1;
     int out_flags = 0;
     double *last_sums = nullptr; // device pointer actually used by the last run
@@ -400,6 +401,11 @@ int swk_set_sequence(swk_engine *e, const swk_params *p, const swk_tables *t)
     L.n_tl = (uint32_t)tl_time.size();
     L.tl_time = put(b, tl_time.empty() ? (const void *)&zero : tl_time.data(), tl_time.size() * 4);
     L.tl_mask = put(b, tl_mask.empty() ? (const void *)&zero : tl_mask.data(), tl_mask.size() * 4);
+    std::vector<uint32_t> tl_run(tl_time.size(), 0u); // gradient-only entries at consecutive timepoints (e.g. a PGSE lobe)
+    for (size_t i = tl_time.size(); i-- > 0;)
+        if (tl_mask[i] == EV_GRAD)
+            tl_run[i] = (i + 1 < tl_time.size() && tl_mask[i + 1] == EV_GRAD && tl_time[i + 1] == tl_time[i] + 1) ? tl_run[i + 1] + 1u : 1u;
+    L.tl_run = put(b, tl_run.empty() ? (const void *)&zero : tl_run.data(), tl_run.size() * 4);
     L.n_rf = t->n_RF;
     L.rf_s = put(b, rf_s.data(), rf_s.size() * 4);
     L.rf_c = put(b, rf_c.data(), rf_c.size() * 4);
@@ -488,6 +494,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         return fail(e, SWK_ERR_SUBSTRATE, msg);
     }
     if ((uint64_t)e->spin_first + e->n_local > e->P.n_spins) return fail(e, SWK_ERR_INVALID, "spin shard exceeds the global number of spins");
+    if (e->host_rows && e->host_row_first + e->n_local > e->host_rows) return fail(e, SWK_ERR_INVALID, "swk_set_host_rows: this engine's rows exceed the host arrays");
     for (uint32_t i = 0; i < n_scales; i++)
         if (scale_type == SWK_SCALE_FOV && !(scales[i] > 0.f)) return fail(e, SWK_ERR_INVALID, "FoV scales must be positive");
     CK(cudaSetDevice(e->device));
@@ -616,8 +623,8 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     const size_t bsum_bytes = A.sums ? E * ns * 4 * sizeof(float) : 0;
     const size_t smem_cap = std::min<size_t>(e->smem_optin, 96 * 1024);
     if (bsum_bytes > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
-    A.blob_in_smem = (e->L.bytes + bsum_bytes + 3 * ns * sizeof(float) <= smem_cap) ? 1 : 0;
-    const size_t sgt_bytes = (mode == SWK_MODE_FAST) ? 3 * ns * sizeof(float) : 0;
+    A.blob_in_smem = (e->L.bytes + bsum_bytes + (3 * ns + 3) * sizeof(float) <= smem_cap) ? 1 : 0;
+    const size_t sgt_bytes = (mode == SWK_MODE_FAST) ? (3 * ns + 3) * sizeof(float) : 0;
     const size_t smem = (A.blob_in_smem ? e->L.bytes : 0) + bsum_bytes + sgt_bytes;
     if (mode == SWK_MODE_FAST && (uint64_t)A.V >= (1ull << 32)) return fail(e, SWK_ERR_INVALID, "SWK_MODE_FAST indexes voxels with 32 bits: phantom too large");
     if (mode == SWK_MODE_FAST && std::max(A.nx, std::max(A.ny, A.nz)) > (1u << 20)) return fail(e, SWK_ERR_INVALID, "SWK_MODE_FAST: more than 2^20 voxels along one axis");
@@ -627,10 +634,17 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     if (mode == SWK_MODE_COMPAT) kern = stats_on ? walk_kernel<SWK_MODE_COMPAT, true> : walk_kernel<SWK_MODE_COMPAT, false>;
     else {
         const int vox = A.packed ? VOX_PACKED : (A.fieldmap ? VOX_SPLIT : VOX_MASK);
-#define SWK_PICK(V) (A.record ? (stats_on ? walk_fast_kernel<true, true, V> : walk_fast_kernel<false, true, V>) \
-                              : (stats_on ? walk_fast_kernel<true, false, V> : walk_fast_kernel<false, false, V>))
+        bool gruns = false; // does the timeline hold a run of gradient samples (swk_set_sequence: tl_run >= 2)?
+        {
+            const uint32_t *run = reinterpret_cast<const uint32_t *>(e->blob_h.data() + e->L.tl_run);
+            for (uint32_t i = 0; i < e->L.n_tl; i++) gruns |= run[i] >= 2u;
+        }
+#define SWK_PICK2(V, G) (A.record ? (stats_on ? walk_fast_kernel<true, true, V, G> : walk_fast_kernel<false, true, V, G>) \
+                                  : (stats_on ? walk_fast_kernel<true, false, V, G> : walk_fast_kernel<false, false, V, G>))
+#define SWK_PICK(V) (gruns ? SWK_PICK2(V, true) : SWK_PICK2(V, false))
         kern = vox == VOX_PACKED ? SWK_PICK(VOX_PACKED) : (vox == VOX_SPLIT ? SWK_PICK(VOX_SPLIT) : SWK_PICK(VOX_MASK));
 #undef SWK_PICK
+#undef SWK_PICK2
     }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
 
@@ -662,20 +676,21 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     if (host && n_slices > 1) { // rows [j_first, j_end) of every scale: one strided copy per array and slice
         for (uint32_t i = 0; i < n_slices; i++) {
             const size_t r0 = (size_t)i * slice_len, r1 = std::min<size_t>(S, r0 + slice_len);
+            const size_t HS = e->host_rows ? (size_t)e->host_rows : S, h0 = (e->host_rows ? (size_t)e->host_row_first : 0) + r0; // host pitch / first row
             CK(cudaStreamWaitEvent(e->dstream, e->ev_slice[i], 0));
             if (host->M1 && e->M1.p) {
                 const size_t row = E * 3 * sizeof(float);
-                if (row) CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->M1) + r0 * row, S * row, static_cast<char *>(e->M1.p) + r0 * row, S * row,
+                if (row) CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->M1) + h0 * row, HS * row, static_cast<char *>(e->M1.p) + r0 * row, S * row,
                                               (r1 - r0) * row, K, cudaMemcpyDeviceToHost, e->dstream));
             }
             if (host->XYZ1 && e->XYZ1.p) {
                 const size_t row = e->trj * 3 * sizeof(float);
-                CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->XYZ1) + r0 * row, S * row, static_cast<char *>(e->XYZ1.p) + r0 * row, S * row,
+                CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->XYZ1) + h0 * row, HS * row, static_cast<char *>(e->XYZ1.p) + r0 * row, S * row,
                                      (r1 - r0) * row, K, cudaMemcpyDeviceToHost, e->dstream));
             }
             if (host->T && e->T.p) {
                 const size_t row = E;
-                if (row) CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->T) + r0 * row, S * row, static_cast<char *>(e->T.p) + r0 * row, S * row,
+                if (row) CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->T) + h0 * row, HS * row, static_cast<char *>(e->T.p) + r0 * row, S * row,
                                               (r1 - r0) * row, K, cudaMemcpyDeviceToHost, e->dstream));
             }
         }
@@ -720,9 +735,19 @@ int swk_download(swk_engine *e, float *M1, float *XYZ1, uint8_t *T)
     if (e->n_scales == 0) return fail(e, SWK_ERR_STATE, "swk_download: nothing has been run");
     if ((M1 && !e->M1.p) || (XYZ1 && !e->XYZ1.p) || (T && !e->T.p)) return fail(e, SWK_ERR_STATE, "swk_download: output was not requested in the run flags");
     CK(cudaSetDevice(e->device));
-    if (M1) CK(cudaMemcpyAsync(M1, e->M1.p, e->M1.bytes, cudaMemcpyDeviceToHost, e->stream));
-    if (XYZ1) CK(cudaMemcpyAsync(XYZ1, e->XYZ1.p, e->XYZ1.bytes, cudaMemcpyDeviceToHost, e->stream));
-    if (T) CK(cudaMemcpyAsync(T, e->T.p, e->T.bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (!e->host_rows) {
+        if (M1) CK(cudaMemcpyAsync(M1, e->M1.p, e->M1.bytes, cudaMemcpyDeviceToHost, e->stream));
+        if (XYZ1) CK(cudaMemcpyAsync(XYZ1, e->XYZ1.p, e->XYZ1.bytes, cudaMemcpyDeviceToHost, e->stream));
+        if (T) CK(cudaMemcpyAsync(T, e->T.p, e->T.bytes, cudaMemcpyDeviceToHost, e->stream));
+    } else { // rows [host_row_first, +n_local) of every scale of the caller's global arrays
+        const size_t K = e->n_scales, S = e->n_local, HS = (size_t)e->host_rows, h0 = (size_t)e->host_row_first;
+        const size_t rows[3] = {(size_t)e->n_te * 3 * sizeof(float), (size_t)e->trj * 3 * sizeof(float), (size_t)e->n_te};
+        char *dst[3] = {reinterpret_cast<char *>(M1), reinterpret_cast<char *>(XYZ1), reinterpret_cast<char *>(T)};
+        const char *src[3] = {static_cast<const char *>(e->M1.p), static_cast<const char *>(e->XYZ1.p), static_cast<const char *>(e->T.p)};
+        for (int a = 0; a < 3; a++)
+            if (dst[a] && rows[a])
+                CK(cudaMemcpy2DAsync(dst[a] + h0 * rows[a], HS * rows[a], src[a], S * rows[a], S * rows[a], K, cudaMemcpyDeviceToHost, e->stream));
+    }
     CK(cudaStreamSynchronize(e->stream));
     return SWK_OK;
 }
@@ -767,6 +792,26 @@ int swk_run(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_fir
     if (sums && (rc = swk_get_sums(e, sums)) != SWK_OK) return rc;
     if (stats) *stats = e->stats;
     return SWK_OK;
+}
+
+int swk_set_host_rows(swk_engine *e, uint64_t n_rows_total, uint64_t row_first)
+{
+    if (!e) return SWK_ERR_INVALID;
+    e->host_rows = n_rows_total;
+    e->host_row_first = n_rows_total ? row_first : 0;
+    return SWK_OK;
+}
+
+int swk_alloc_pinned(void **ptr, size_t bytes)
+{
+    if (!ptr) return SWK_ERR_INVALID;
+    *ptr = nullptr;
+    return cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) == cudaSuccess ? SWK_OK : SWK_ERR_MEMORY;
+}
+
+void swk_free_pinned(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
 }
 
 int swk_probe_gather(swk_engine *e, uint32_t threads_per_sm, uint32_t iters, double *gathers_per_s, uint64_t *table_bytes)

@@ -137,7 +137,8 @@ __device__ __forceinline__ uint32_t ldg_voxel(const uint32_t *p)
 // together), 2 = one packed 32-bit word (field with its 4 low mantissa bits replaced by the substrate id).
 enum { VOX_MASK = 0, VOX_SPLIT = 1, VOX_PACKED = 2 };
 
-template <bool STATS, bool RECORD, int VOX>
+// GRUNS: the sequence holds runs of gradient samples (taken inside the inner loop); sequences without them get a kernel without that code.
+template <bool STATS, bool RECORD, int VOX, bool GRUNS>
 __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(const __grid_constant__ WalkArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -189,6 +190,10 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
             const double ih = ax == 0 ? inv_h[0] : (ax == 1 ? inv_h[1] : inv_h[2]);
             sgt[i] = (float)(tsig[i / 3u] * ih / (double)fscale * (double)(1u << f));
         }
+        if (threadIdx.x < 3u) { // metres per fixed-point unit x (1e-3 dt 1e-6 gamma 180/pi), kernels.cu:185
+            const double ih = threadIdx.x == 0 ? inv_h[0] : (threadIdx.x == 1 ? inv_h[1] : inv_h[2]);
+            sgt[3u * L.n_sub + threadIdx.x] = (float)((double)fscale / (ih * (double)(1u << f)) * 1e-3 * (double)A.timestep_us * 1e-6 * kGamma * kRad2Deg);
+        }
     }
     __syncthreads();
     // metres per fixed-point unit at this scale (events and outputs only)
@@ -196,7 +201,9 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
                               (double)fscale / (inv_h[2] * (double)(1u << fb))};
 
     const int32_t  *tl_time = blob_ptr<int32_t>(B, L.tl_time);
-    const uint32_t *tl_mask = blob_ptr<uint32_t>(B, L.tl_mask);
+    const uint32_t *tl_mask = blob_ptr<uint32_t>(B, L.tl_mask), *tl_run = blob_ptr<uint32_t>(B, L.tl_run);
+    const float *gtx = blob_ptr<float>(B, L.gx), *gty = blob_ptr<float>(B, L.gy), *gtz = blob_ptr<float>(B, L.gz);
+    const float *umk = sgt + 3u * L.n_sub; // degrees of phase per (mT/m x fixed-point unit) and axis, for gradient runs
     const float *tT1 = blob_ptr<float>(B, L.T1s), *tT2 = blob_ptr<float>(B, L.T2s), *tpXY = blob_ptr<float>(B, L.pXY);
 
     // ---- which spin ----
@@ -273,10 +280,20 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
         float acc = 0.f;
         bool fresh = true; // only for the STATS counters (ind_old = matrix_length+1, kernels.cu:123)
 
-        for (uint32_t ev = 0; ev <= L.n_tl; ev++) {
+        // The timeline is walked entry by entry: steps up to and including the entry's timepoint, then its events.  A RUN of
+        // gradient-only samples at consecutive timepoints (a PGSE lobe: one sample per step for 10 ms) is taken in one go
+        // instead: the plain steps before its first timepoint (part 0), then one step + one gradient sample per timepoint inside
+        // the inner loop itself (part 1) — no segment restart per sample.
+        for (uint32_t ev = 0; ev <= L.n_tl;) {
             const uint32_t ev_time = ev < L.n_tl ? (uint32_t)tl_time[ev] : n_tp;
-            const uint32_t t_stop = ev_time < n_tp ? ev_time + 1u : n_tp;
-            int rem = alive ? (int)(t_stop - t) : 0; // accepted steps still to take before the next event
+            const uint32_t run = ev < L.n_tl ? tl_run[ev] : 0u;
+            const bool is_run = GRUNS && run >= 2u && ev_time < n_tp;
+            const uint32_t run_len = is_run ? min(run, n_tp - ev_time) : 0u;
+          for (int part = 0; part < (is_run ? 2 : 1); part++) {
+            const bool grun = GRUNS && part == 1;
+            const uint32_t t_stop = is_run ? (grun ? ev_time + run_len : ev_time) : (ev_time < n_tp ? ev_time + 1u : n_tp);
+            const uint32_t grad_first = cnt_grad;
+            int rem = alive ? (int)(t_stop - t) : 0; // accepted steps still to take in this part
 
             // =============================== inner loop ===============================
             // one attempt = one tentative step (kernels.cu:130-170).  `overlap` is independent work (random numbers of later
@@ -331,6 +348,11 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
                 p0 = q0; p1 = q1; p2 = q2;
                 acc += field; // kernels.cu:171-172
                 itr = 0;
+                if (GRUNS && grun) { // gradient sample of this timepoint, at the NEW position (kernels.cu:181-187); FP32 here, FP64 in the event path
+                    const float gx = __fmul_rn(gtx[cnt_grad], gscale), gy = __fmul_rn(gty[cnt_grad], gscale), gz = __fmul_rn(gtz[cnt_grad], gscale);
+                    acc += gx * ((float)p0 * umk[0]) + gy * ((float)p1 * umk[1]) + gz * ((float)p2 * umk[2]);
+                    cnt_grad++;
+                }
                 if (RECORD) { // kernels.cu:218-221 (diagnostic mode)
                     if (X1) {
                         float *slot = X1 + 3 * ((size_t)scan * n_tp + (t_stop - (uint32_t)rem));
@@ -353,7 +375,10 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
                 blk++;
             }
             t = t_stop - (uint32_t)rem;
+            if (grun) cnt_grad = grad_first + run_len; // also for lanes that are no longer alive
+          }
             // ============================ end of inner loop ============================
+            if (is_run) { ev += run_len; continue; } // (a run clipped by the end of the TR is followed by entries >= n_tp only)
             if (ev >= L.n_tl) break;
             if (ev_time >= n_tp) break;
 
@@ -412,6 +437,7 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
                 }
                 cur_te++;
             }
+            ev++;
         }
         if (alive) { // end of TR (kernels.cu:226-231)
             const float dt_s = (float)((double)((n_tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);

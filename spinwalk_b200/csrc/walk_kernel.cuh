@@ -41,6 +41,7 @@ enum : uint32_t { EV_DEPH = 1u, EV_GRAD = 2u, EV_RF = 4u, EV_ECHO = 8u };
 struct BlobLayout {
     uint32_t bytes;
     uint32_t tl_time, tl_mask, n_tl;        // merged event timeline: int32 time, uint32 mask
+    uint32_t tl_run;                        // uint32 per entry: length of the run of gradient-only entries at consecutive timepoints starting here (else 0)
     uint32_t rf_s, rf_c, rf_ph, n_rf;       // float sin/cos of flip angle, phase (deg); entry 0 unused
     uint32_t deph_deg, n_deph;              // float
     uint32_t gx, gy, gz, n_grad;            // float mT/m (unscaled)

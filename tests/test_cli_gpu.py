@@ -1,0 +1,119 @@
+"""The drop-in host: `bin/spinwalk sim -c x.ini` (host/main.cpp -> sim_driver.cpp -> C-ABI) on real files.
+
+A phantom HDF5 file (written by host/h5lite.cpp) + an INI in the reference's syntax go in; the output HDF5 file must hold
+the reference's datasets (monte_carlo.cu:168-197) with, in --compat mode, exactly the arrays the reference's own cu_sim
+kernel produces for the same inputs (T and XYZ bitwise, M to 2e-6) — positions included, because the host seeds
+std::mt19937 the way monte_carlo.cu:142-151 does."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import h5util
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(h5util.ROOT, "bin", "spinwalk")
+
+INI = """[GENERAL]
+SEQ_NAME = se_test
+[FILES]
+OUTPUT_DIR = ./out
+PHANTOM[0] = ./phantom.h5
+[TISSUE_PARAMETERS]
+DIFFUSIVITY[0] = 1.0e-9
+DIFFUSIVITY[1] = 1.0e-9
+P_XY[0] = 1.0 0.0
+P_XY[1] = 0.0 1.0
+T1[0] = 2200
+T1[1] = 2200
+T2[0] = 41
+T2[1] = 41
+[SCAN_PARAMETERS]
+TR = 40000
+TE = 20000
+RF_FA = 90.0 180.0
+RF_PH = 0.0 90
+RF_T = 0 10000
+TIME_STEP = 50
+DUMMY_SCAN = 0
+[SIMULATION_PARAMETERS]
+B0 = 9.4
+SEED = 10
+NUMBER_OF_SPINS = {S}
+CROSS_FOV = 0
+RECORD_TRAJECTORY = 0
+MAX_ITERATIONS = 1e4
+WHAT_TO_SCALE = 0
+SCALE[0] = 0.1
+SCALE[1] = 1.0
+SCALE[2] = 8.0
+"""
+
+
+@pytest.fixture(scope="module")
+def cli():
+    subprocess.run(["make", "-s", "-C", os.path.join(h5util.ROOT, "host")], check=True)
+    assert os.path.exists(BIN), "bin/spinwalk was not built (needs spinwalk_b200/libspinwalk_b200.so)"
+    return BIN
+
+
+def _stage(tmp_path, S, int8_mask=False):
+    case, mask, fm, fov, xyz0 = cases.se(n_spins=S)
+    h5util.write(str(tmp_path / "phantom.h5"), {"fieldmap": fm, "mask": mask.astype(np.int8) if int8_mask else mask, "fov": np.asarray(fov, np.float32),
+                                                "bvf": np.array([8.0], np.float32)})
+    (tmp_path / "se.ini").write_text(INI.format(S=S))
+    return case, mask, fm, fov, xyz0
+
+
+def test_cli_compat_equals_reference_kernel(cli, oracle, tmp_path):
+    if not oracle.have_ref_cuda():
+        pytest.skip("oracle/_ref/libswref_cuda.so not present")
+    S = 2048
+    case, mask, fm, fov, xyz0 = _stage(tmp_path, S, int8_mask=True)  # int8 mask as MATLAB / h5py users write it (README.md:145-163)
+    r = subprocess.run([cli, "sim", "-c", str(tmp_path / "se.ini"), "--compat", "--sums"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Simulation completed successfully" in r.stdout
+    out = str(tmp_path / "out" / "se_test_phantom.h5")
+    assert sorted(h5util.names(out)) == ["M", "T", "TE", "XYZ", "scales", "sums"]
+    # the INI route rounds DIFFUSIVITY through float (std::stof, config_reader.cpp:164), as the reference does
+    case.diffusivity = [float(np.float32(1.0e-9))] * 2
+    ref = oracle.run_ref_cuda(case, fm, mask, xyz0)  # xyz0 = the oracle's restatement of the mt19937 start positions
+    M, X, T = h5util.read(out, "M"), h5util.read(out, "XYZ"), h5util.read(out, "T")
+    assert M.shape == (3, S, 1, 3) and X.shape == (3, S, 1, 3) and T.shape == (3, S, 1, 1) and T.dtype == np.uint8
+    assert np.array_equal(T[..., 0], ref["T"])
+    assert np.array_equal(X.view(np.uint32), ref["XYZ1"].view(np.uint32))
+    assert np.abs(M - ref["M1"]).max() <= 2e-6
+    assert np.array_equal(h5util.read(out, "scales").ravel(), np.array([0.1, 1.0, 8.0], np.float32))
+    assert np.allclose(h5util.read(out, "TE").ravel(), [0.02])
+    sums = h5util.read(out, "sums")
+    assert sums.shape == (3, 1, 2, 4) and sums[..., 3].sum() == 3 * S
+
+
+def test_cli_two_engines_equal_one(cli, tmp_path):
+    """-d 0,0: two engines (threads) share the host arrays through swk_set_host_rows; the spins are keyed by their global id,
+    so the output file equals the single-engine one bit for bit (fast mode)."""
+    S = 3001
+    _stage(tmp_path, S)
+    outs = []
+    for dev in ("0", "0,0"):
+        r = subprocess.run([cli, "sim", "-c", str(tmp_path / "se.ini"), "-d", dev, "-q"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = str(tmp_path / "out" / "se_test_phantom.h5")
+        outs.append({k: h5util.read(out, k) for k in ("M", "XYZ", "T")})
+    for k in ("M", "XYZ", "T"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    assert (outs[0]["M"] != 0).any()
+
+
+def test_cli_error_conventions(cli, tmp_path):
+    _stage(tmp_path, 64)
+    r = subprocess.run([cli, "sim", "-c", str(tmp_path / "se.ini"), "-p"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU path" in r.stderr
+    r = subprocess.run([cli, "sim", "-c", str(tmp_path / "missing.ini")], capture_output=True, text=True)
+    assert r.returncode == 1 and "does not exist" in r.stderr
+    (tmp_path / "one.ini").write_text(INI.format(S=64).replace("DIFFUSIVITY[1] = 1.0e-9\n", "").replace("T1[1] = 2200\n", "").replace("T2[1] = 41\n", "")
+                                      .replace("P_XY[0] = 1.0 0.0\nP_XY[1] = 0.0 1.0", "P_XY[0] = 1.0"))
+    r = subprocess.run([cli, "sim", "-c", str(tmp_path / "one.ini")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Simulation failed" in r.stderr and "substrate" in r.stderr  # monte_carlo.cu:113-118
