@@ -75,6 +75,7 @@ struct swk_engine {
 
     // spins
     DevBuf xyz0, m0, order;
+    DevBuf state_a, state_b, state_vox;                     // re-binning pauses of long runs: per (scale, spin) walker state
     DevBuf sort_keys_in, sort_keys_out, sort_ids, sort_tmp; // kept between runs: re-sorting after every swk_set_spins must not malloc
     bool order_valid = false;
     uint32_t order_slice = 0; // slice length the order was built for (0 = one slice)
@@ -210,6 +211,19 @@ __global__ void __launch_bounds__(256) gather_probe_kernel(const uint32_t *tab, 
     if (acc == 0x12345678u) sink[0] = acc;
 }
 
+// Re-binning keys of a paused long run: like sort_keys_kernel, but from the walkers' CURRENT voxel (state_vox) and substrate,
+// one segment per scale (the scale index leads the key) when the walks differ between scales.
+__global__ void rebin_keys_kernel(const uint32_t *state_vox, const uint4 *state_b, uint32_t n_local, uint32_t n_seg, uint32_t ny, uint32_t nz,
+                                  uint64_t *keys, uint32_t *ids)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_seg * n_local) return;
+    const uint32_t v = state_vox[i], ts = state_b[i].w & 0xffu;
+    const uint32_t vz = v % nz, vy = (v / nz) % ny, vx = v / (nz * ny);
+    keys[i] = ((uint64_t)(i / n_local) << 56) | ((uint64_t)(255u - ts) << 48) | (spread3(vx) << 2) | (spread3(vy) << 1) | spread3(vz);
+    ids[i] = (uint32_t)(i % n_local);
+}
+
 bool ascending(const int32_t *t, uint32_t n)
 {
     for (uint32_t i = 1; i < n; i++)
@@ -277,7 +291,7 @@ void swk_destroy(swk_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     for (DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp})
+                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox})
         release(*b);
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -650,12 +664,70 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
 
     if ((((uint64_t)slice_len + kBlock - 1) / kBlock) * K > 0x7fffffffull) return fail(e, SWK_ERR_INVALID, "too many spins x scales for one launch");
     CK(cudaEventRecord(e->ev0, e->stream));
+    A.scan_first = 0;
+    A.scan_end = A.n_scans;
     if (n_slices == 1) {
         A.j_first = 0;
         A.j_end = (uint32_t)S;
         const uint64_t grid = ((S + kBlock - 1) / kBlock) * K;
-        kern<<<(unsigned)grid, kBlock, smem, e->stream>>>(A);
-        CK(cudaGetLastError());
+        // ---- long runs (bSSFP: ~1000 TRs): pause at TR boundaries and re-sort the spins by their CURRENT voxel ----
+        // The start order keeps the resident spins' voxels inside L2 only while they have not diffused apart: after n steps the
+        // cloud has grown by ~2 sigma_vox sqrt(n) voxels per axis.  A pause every (35 / sigma_vox)^2 steps keeps that growth below
+        // ~70 voxels (measured on C4: 2.26e11 steps/s at 60 TRs per leg, 2.13e11 at 125, 2.01e11 at 250, 1.65e11 without); it costs one 36-byte state record per walker and one radix sort.  Small FoV scales (sigma_vox > 2) touch the
+        // table at random whatever the order and are not re-binned.
+        uint32_t scans_per_leg = A.n_scans;
+        bool per_scale = false;
+        if (mode == SWK_MODE_FAST && A.order && !A.record && !(flags & SWK_RUN_NO_REBIN) && A.n_scans > 1) {
+            double sig_vox = 0.;
+            const double *sig = reinterpret_cast<const double *>(e->blob_h.data() + e->L.sigma);
+            for (uint32_t k = 0; k < n_scales; k++)
+                for (uint32_t sub = 0; sub < ns; sub++)
+                    for (int i = 0; i < 3; i++)
+                        sig_vox = std::max(sig_vox, sig[sub] * (double)e->dims[i] / ((double)e->fov[i] * (scale_type == SWK_SCALE_FOV ? (double)scales[k] : 1.)));
+            const double n_rb = sig_vox > 0. ? (35. / sig_vox) * (35. / sig_vox) : 1e30;
+            const double total = (double)A.n_scans * A.n_tp;
+            per_scale = scale_type == SWK_SCALE_FOV && K > 1; // the walks differ between scales only when the FoV is scaled
+            if (sig_vox <= 2. && total >= 2. * n_rb && (!per_scale || K * S <= (1ull << 29)))
+                scans_per_leg = (uint32_t)std::max(1., std::floor(n_rb / A.n_tp));
+            if (const char *ev = getenv("SWK_REBIN_SCANS")) scans_per_leg = (uint32_t)std::max(1, atoi(ev)); // tuning knob
+        }
+        if (scans_per_leg < A.n_scans) {
+            const size_t n_state = K * S, n_seg = per_scale ? K : 1, n_sort = n_seg * S;
+            if ((rc = ensure(e, e->state_a, n_state * sizeof(uint4))) != SWK_OK || (rc = ensure(e, e->state_b, n_state * sizeof(uint4))) != SWK_OK ||
+                (rc = ensure(e, e->state_vox, n_state * sizeof(uint32_t))) != SWK_OK || (rc = ensure(e, e->sort_keys_in, n_sort * 8)) != SWK_OK ||
+                (rc = ensure(e, e->sort_keys_out, n_sort * 8)) != SWK_OK || (rc = ensure(e, e->sort_ids, n_sort * 4)) != SWK_OK)
+                return rc;
+            A.state_a = static_cast<uint4 *>(e->state_a.p);
+            A.state_b = static_cast<uint4 *>(e->state_b.p);
+            A.state_vox = static_cast<uint32_t *>(e->state_vox.p);
+            DevBuf order2; // the re-binned order lives in its own buffer: e->order keeps the start order for the next run
+            struct Free { DevBuf &b; ~Free() { release(b); } } free_order2{order2};
+            if ((rc = ensure(e, order2, n_sort * sizeof(uint32_t))) != SWK_OK) return rc;
+            for (uint32_t s0 = 0; s0 < A.n_scans; s0 += scans_per_leg) {
+                A.scan_first = s0;
+                A.scan_end = std::min(A.n_scans, s0 + scans_per_leg);
+                kern<<<(unsigned)grid, kBlock, smem, e->stream>>>(A);
+                CK(cudaGetLastError());
+                if (A.scan_end == A.n_scans) break;
+                rebin_keys_kernel<<<(unsigned)((n_sort + 255) / 256), 256, 0, e->stream>>>(A.state_vox, A.state_b, (uint32_t)S, (uint32_t)n_seg, A.ny, A.nz,
+                                                                                         static_cast<uint64_t *>(e->sort_keys_in.p), static_cast<uint32_t *>(e->sort_ids.p));
+                CK(cudaGetLastError());
+                size_t tmp_bytes = 0;
+                CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, static_cast<uint64_t *>(e->sort_keys_in.p), static_cast<uint64_t *>(e->sort_keys_out.p),
+                                                   static_cast<uint32_t *>(e->sort_ids.p), static_cast<uint32_t *>(order2.p), (int)n_sort, 0, 64, e->stream));
+                if ((rc = ensure(e, e->sort_tmp, std::max(tmp_bytes, e->sort_tmp.bytes))) != SWK_OK) return rc;
+                CK(cub::DeviceRadixSort::SortPairs(e->sort_tmp.p, tmp_bytes, static_cast<uint64_t *>(e->sort_keys_in.p), static_cast<uint64_t *>(e->sort_keys_out.p),
+                                                   static_cast<uint32_t *>(e->sort_ids.p), static_cast<uint32_t *>(order2.p), (int)n_sort, 0, 64, e->stream));
+                A.order = static_cast<const uint32_t *>(order2.p);
+                A.order_per_scale = per_scale ? 1 : 0;
+                extra_launches += 2;
+            }
+            extra_launches += (A.n_scans + scans_per_leg - 1) / scans_per_leg - 1; // n_launches below counts one walk launch per slice
+            CK(cudaStreamSynchronize(e->stream)); // order2 is freed on return
+        } else {
+            kern<<<(unsigned)grid, kBlock, smem, e->stream>>>(A);
+            CK(cudaGetLastError());
+        }
     } else {
         // slice i runs on compute stream i & 1 (tails overlap the next slice); its rows are downloaded as soon as it is done
         const bool one_stream = getenv("SWK_ONE_CSTREAM") != nullptr; // tuning knob
@@ -847,7 +919,7 @@ uint64_t swk_device_bytes(const swk_engine *e)
     if (!e) return 0;
     uint64_t n = 0;
     for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp})
+                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox})
         n += b->bytes;
     return n;
 }

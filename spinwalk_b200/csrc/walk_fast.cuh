@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
     // ---- which spin ----
     const uint32_t j = A.j_first + (blockIdx.x / A.n_scales) * kBlock + threadIdx.x;
     bool alive = j < A.j_end;
-    const uint32_t jl = alive ? (A.order ? __ldg(A.order + j) : j) : 0u;
+    const uint32_t jl = alive ? (A.order ? __ldg(A.order + (A.order_per_scale ? (size_t)k * A.n_local : 0) + j) : j) : 0u;
     const uint32_t spin_no = A.spin_first + jl; // GLOBAL spin id: RNG key and dephasing term
 
     float m[3] = {0.f, 0.f, 1.f};
@@ -230,9 +230,23 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
         }
         p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
     }
+    // ---- resuming a long run after a re-binning pause (engine.cu: run_impl): position, magnetisation, substrate and RNG
+    //      block counter come back from the state arrays; everything else of the per-TR state is reset at a TR start anyway ----
+    uint32_t blk = 0;
+    const size_t st_idx = (size_t)k * A.n_local + jl;
+    if (A.scan_first > 0 && alive) {
+        const uint4 sa = A.state_a[st_idx], sb = A.state_b[st_idx];
+        p0 = sa.x; p1 = sa.y; p2 = sa.z; blk = sa.w;
+        m[0] = __uint_as_float(sb.x); m[1] = __uint_as_float(sb.y); m[2] = __uint_as_float(sb.z);
+    }
     const uint32_t ny = A.ny, nz = A.nz;
     uint32_t ind_cur = ((p0 >> fb) * ny + (p1 >> fb)) * nz + (p2 >> fb);
     uint32_t ts_old = alive ? (uint32_t)__ldg(A.mask + ind_cur) : 0u;
+    if (A.scan_first > 0 && alive) {
+        const uint32_t meta = A.state_b[st_idx].w; // substrate | lost << 8
+        ts_old = meta & 0xffu;
+        if (meta & 0x100u) alive = false; // lost in an earlier launch (already counted there)
+    }
     const bool has_field = VOX != VOX_MASK;
     const float field_k = A.field_k;
     // The reference loads field / T1 / T2 at the first accepted step (kernels.cu:91,150-170).  Holding the field of
@@ -260,12 +274,11 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
 
     const uint32_t n_tp = A.n_tp;
     // One Philox block feeds TWO attempts: the even attempt of block `blk` steps by (na*), the odd one by (nb*).
-    uint32_t blk = 0;
     const uint32_t kOne = A.one_bits; // 0x3f800000, deliberately opaque to ptxas (see and_or)
     float na0, na1, na2, nb0, nb1, nb2;
     normals6_fast(philox_fixed(blk, seed_lo, spin_no, seed_hi_walk), kOne, na0, na1, na2, nb0, nb1, nb2);
 
-    for (uint32_t scan = 0; scan < A.n_scans; scan++) {
+    for (uint32_t scan = A.scan_first; scan < A.scan_end; scan++) {
         const bool last_scan = (scan + 1 == A.n_scans);
         { // phase cycling + first RF (kernels.cu:110-120)
             float ph = (float)((double)(A.rf_ph0 + (float)scan * lin_pc) + (double)(scan * (scan + 1u)) / 2.0 * (double)A.quad_pc);
@@ -446,7 +459,14 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
     }
 
     // ---- final position (kernels.cu:220-221 leaves the last committed position in xyz1) ----
-    if (!RECORD && X1 && j < A.j_end) {
+    if (A.scan_end < A.n_scans) { // pause at a TR boundary: (na*, nb*) are the untouched normals of block `blk`, so the counter is the whole RNG state
+        if (j < A.j_end) {
+            A.state_a[st_idx] = make_uint4(p0, p1, p2, blk);
+            A.state_b[st_idx] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts_old | ((alive ? 0u : 1u) << 8));
+            A.state_vox[st_idx] = ((p0 >> fb) * ny + (p1 >> fb)) * nz + (p2 >> fb);
+        }
+    }
+    if (!RECORD && X1 && j < A.j_end && A.scan_end == A.n_scans) {
         X1[0] = (float)((double)p0 * unit_m[0]); X1[1] = (float)((double)p1 * unit_m[1]); X1[2] = (float)((double)p2 * unit_m[2]);
     }
 

@@ -76,6 +76,11 @@ struct WalkArgs {
     const float *m0;         // [n_local][3] or nullptr => (0,0,1)
     const uint32_t *order;   // nullptr, or thread j simulates local spin order[j] (locality sort)
     uint32_t spin_first, n_local;
+    // long runs (many TRs) are paused at TR boundaries to re-sort the spins by their CURRENT voxel (FAST mode, engine.cu run_impl)
+    uint32_t scan_first, scan_end; // this launch simulates scans [scan_first, scan_end) of n_scans
+    int32_t  order_per_scale;      // order holds one permutation per scale: [n_scales][n_local]
+    uint4   *state_a, *state_b;    // [n_scales][n_local]: (p0, p1, p2, RNG block counter), (Mx, My, Mz, substrate | lost << 8)
+    uint32_t *state_vox;           // [n_scales][n_local]: linear voxel index at the pause (sort key of the next launch)
     uint32_t j_first, j_end; // this launch simulates thread slots [j_first, j_end) of the shard (pipelined host runs launch slices)
     // outputs (any may be nullptr), reference layouts restricted to the shard
     float   *M1;             // [K][n_local][E][3]
