@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — spin-steps/s of the `sim` hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c3r|c4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c3r|c4|c5]
 
 A "step" is one pass of the hot path over the whole workload: all spins x all scales x all
 timepoints of one phantom (what one iteration of the reference's phantom loop does,
@@ -54,6 +54,11 @@ def workload(name: str, n_spins: int | None, n_scales: int | None):
                    linear_phase_cycling=180.0, scales=[1.0])
         ph = dict(kind="cylinder", n=600, fov_um=600.0, radius_um=8.0, bvf=4.0, Y=0.78, seed=0)
         S, desc = 10_000_000, "C4 bSSFP (config/ssfp.ini), 1101 TRs x 200 steps, 600^3 cylinder phantom, 1e7 spins, 1 scale"
+    elif name == "c5":
+        cfg = dict(base, TR_us=40000, TE_us=[20000], RF_FA_deg=[90.0], RF_PH_deg=[0.0], RF_T_us=[0])
+        ph = dict(kind="cylinder", n=1000, fov_um=1000.0, radius_um=8.0, bvf=4.0, Y=0.78, seed=0)
+        S, desc = 125_000_000, ("C5 GRE BOLD (config/gre.ini), 1000^3 cylinder phantom r=8um BVF 4% + fieldmap (9 GB per GPU), "
+                                "1.25e8 spins per GPU (1e9 over 8), 50 FoV scales, ensemble sums only (no per-spin outputs)")
     elif name in ("c3", "c3r"):
         from spinwalk_b200.sequences import pgse
 
@@ -270,6 +275,9 @@ def main():
     eng = sw.Engine(local_rank)
     eng.set_phantom(mask_d, fm_d, fov)
     del mask_d, fm_d
+    torch.cuda.empty_cache()
+    per_spin_out = args.workload != "c5"  # C5: 1e9 spins x 50 scales of per-spin output would be 650 GB: the reduce is the product
+    out_flags = sw.OUT_ALL if per_spin_out else 0
     eng.set_sequence(cfg)
     eng.set_spins(xyz0_pin.numpy(), None, spin_first)
     E, ns = cfg.n_TE, cfg.n_substrate
@@ -282,12 +290,12 @@ def main():
         torch.cuda.synchronize(dev)
 
     def one_pass():
-        st = eng.run_device(mode=mode, flags=sw.OUT_ALL, d_sums_ptr=sums_d.data_ptr())
+        st = eng.run_device(mode=mode, flags=out_flags, d_sums_ptr=sums_d.data_ptr())
         sharding.allreduce_sums(sums_d)  # the one collective of the path: a few KB of per-echo ensemble sums (NCCL)
         return st
 
     # counters (voxel changes etc.) for the roofline's algorithmic bytes: same inputs, STATS kernel variant, untimed
-    st_counts = eng.run_device(mode=mode, flags=sw.OUT_ALL | sw.RUN_STATS, d_sums_ptr=sums_d.data_ptr())
+    st_counts = eng.run_device(mode=mode, flags=out_flags | sw.RUN_STATS, d_sums_ptr=sums_d.data_ptr())
 
     for _ in range(args.warmup):
         one_pass()
@@ -313,17 +321,20 @@ def main():
     # ---- end-to-end through swk_run with host buffers
     e2e = None
     if not args.no_e2e:
-        out = (torch.empty((K, S_per_gpu, E, 3), dtype=torch.float32, pin_memory=True),
-               torch.empty((K, S_per_gpu, eng.trj, 3), dtype=torch.float32, pin_memory=True),
-               torch.empty((K, S_per_gpu, E), dtype=torch.uint8, pin_memory=True))
-        out_np = tuple(o.numpy() for o in out)
+        if per_spin_out:
+            out = (torch.empty((K, S_per_gpu, E, 3), dtype=torch.float32, pin_memory=True),
+                   torch.empty((K, S_per_gpu, eng.trj, 3), dtype=torch.float32, pin_memory=True),
+                   torch.empty((K, S_per_gpu, E), dtype=torch.uint8, pin_memory=True))
+            out_np = tuple(o.numpy() for o in out)
+        else:
+            out, out_np = (), None
         h2d = xyz0_pin.numel() * 4 + K * 4
         d2h = sum(o.numel() * o.element_size() for o in out) + K * E * ns * 4 * 8
-        eng.run(xyz0_pin.numpy(), None, spin_first, mode=mode, out=out_np, stats=False)  # warm
+        eng.run(xyz0_pin.numpy(), None, spin_first, mode=mode, out=out_np, outputs=per_spin_out, stats=False)  # warm
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            r = eng.run(xyz0_pin.numpy(), None, spin_first, mode=mode, out=out_np, stats=False)
+            r = eng.run(xyz0_pin.numpy(), None, spin_first, mode=mode, out=out_np, outputs=per_spin_out, stats=False)
             if world > 1:
                 sums_d.copy_(torch.from_numpy(r["sums"]))
                 sharding.allreduce_sums(sums_d)
@@ -334,7 +345,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": total_steps / float(te.item()), "unit": "spin-steps/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * float(te.item()) / args.steps,
-               "api": "swk_run (C-ABI) with pinned host buffers: XYZ0 in; M1, XYZ1, T, sums out"}
+               "api": "swk_run (C-ABI) with pinned host buffers: XYZ0 in; " + ("M1, XYZ1, T, sums out" if per_spin_out else "sums out")}
         del out, out_np
 
     # ---- the voxel fetch's own roofline, measured live on this device and this phantom (untimed diagnostic launch)
@@ -354,7 +365,7 @@ def main():
     except Exception:
         pass
     per_pass_bytes = (st_counts["mask_gathers"] * 1 + st_counts["field_gathers"] * 4
-                      + S_per_gpu * K * (24 + 13 * E + 12))
+                      + S_per_gpu * K * (24 + ((13 * E + 12) if per_spin_out else 0)))
     ker_ms_per_launch = ker_ms / args.steps
     achieved = per_pass_bytes / (ker_ms_per_launch * 1e-3) / 1e9
     fetches_per_s = st_counts["mask_gathers"] / (ker_ms_per_launch * 1e-3)
@@ -380,12 +391,12 @@ def main():
             "config": {"workload": desc, "spins_per_gpu": S_per_gpu, "n_scales": K, "timepoints": cfg.n_timepoints,
                        "scans": eng.n_dummy_scan + 1, "spin_steps_per_pass": steps_per_pass_rank * world,
                        "rng": "philox4x32-10, one block per two steps + Box-Muller (SWK_MODE_FAST)" if mode == sw.MODE_FAST else "minstd_rand + erfcinvf (SWK_MODE_COMPAT, reference arithmetic)",
-                       "l2": "inputs larger than L2 (phantom 1.08 GB vs 126 MB)" if ph["n"] >= 600 else "phantom fits in L2; outputs (12.5 GB > L2) rewritten every pass",
+                       "l2": f"inputs larger than L2 (phantom {5 * ph['n'] ** 3 / 1e9:.2f} GB vs 126 MB)" if ph["n"] >= 600 else "phantom fits in L2; outputs (12.5 GB > L2) rewritten every pass",
                        "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums"},
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": args.steps * st["n_launches"],
             "e2e": e2e, "roofline": roofline, "lost_spins": st_counts["lost"]}
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload != "c5":  # (C5's 5 GB host phantom: use C2's baseline)
         try:
             cb, _, _ = cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0)
             line["cpu_baseline"] = cb
