@@ -196,6 +196,36 @@ def cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0, threads=None):
                       f"low spin ids keep mt19937::discard(seed+spin) cheap, which flatters the CPU reference (SURVEY App. B-3)"}, steps, sec
 
 
+def reference_cuda(cfg_kw, ph, mask2, fm2, fov, device, target_s=10.0):
+    """The reference's EXISTING CUDA kernel (its untouched kernels.cu compiled for sm_100a into oracle/_ref/libswref_cuda.so, launched
+    once per scale with a device sync like monte_carlo.cu:273-337) on a bounded sample of the same workload, same GPU.  Kernel time only
+    (CUDA events around the launches); uploads and downloads of the harness are not counted."""
+    from oracle import pyoracle as po
+
+    if not po.have_ref_cuda():
+        return None
+    n = ph["n"]
+    mask, fm = full_phantom(ph, mask2, fm2)
+
+    def run(n_spins):
+        c = po.Case(fov=tuple(fov), phantom_size=(n, n, n), n_spins=n_spins, TR_us=cfg_kw["TR_us"], timestep_us=cfg_kw["timestep_us"],
+                    seed=cfg_kw["seed"], B0=cfg_kw["B0"], TE_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["TE_us"]],
+                    RF_FA_deg=cfg_kw["RF_FA_deg"], RF_PH_deg=cfg_kw["RF_PH_deg"], RF_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["RF_T_us"]],
+                    n_dummy_scan=cfg_kw.get("n_dummy_scan", 0), linear_phase_cycling=cfg_kw.get("linear_phase_cycling", 0.0),
+                    gradient_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw.get("gradient_T_us", [])],
+                    gradX_mTm=cfg_kw.get("gradient_X_mTm", []), gradY_mTm=cfg_kw.get("gradient_Y_mTm", []), gradZ_mTm=cfg_kw.get("gradient_Z_mTm", []),
+                    diffusivity=cfg_kw["diffusivity"], T1_ms=cfg_kw["T1_ms"], T2_ms=cfg_kw["T2_ms"], pXY=cfg_kw["pXY"],
+                    scales=cfg_kw["scales"], scale_type=cfg_kw["scale_type"], cross_fov=cfg_kw["cross_fov"], max_iterations=cfg_kw["max_iterations"])
+        r = po.run_ref_cuda(c, fm, mask, make_positions(n_spins, fov, cfg_kw["seed"]), device=device)
+        return c.total_steps(), r["kernel_ms"] * 1e-3
+
+    steps, sec = run(200_000)  # calibration (also warms the context up)
+    n_spins = int(min(cfg_kw["n_spins"], 4_000_000, max(200_000, 200_000 * target_s / max(sec, 1e-3))))
+    steps, sec = run(n_spins)
+    return {"value": steps / sec, "unit": "spin-steps/s", "kind": "reference cu_sim (src/sim/kernels.cu:56-63) built for sm_100a, one launch + sync per scale",
+            "sample": f"first {n_spins} spins x all {len(cfg_kw['scales'])} scales of the workload ({steps:.3g} spin-steps, {sec:.2f} s of kernel time)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -402,9 +432,15 @@ def main():
             line["cpu_baseline"] = cb
         except Exception as ex:  # the baseline is a reported extra; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "spin-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    eng.close()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload not in ("c5", "c4"):
+        try:  # the reference's own CUDA kernel on this GPU, for context; never the thing measured above
+            torch.cuda.empty_cache()
+            line["reference_cuda"] = reference_cuda(cfg_kw, ph, mask2, fm2, fov, local_rank)
+        except Exception as ex:
+            line["reference_cuda"] = {"value": None, "sample": f"failed: {ex}"}
     if rank == 0:
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

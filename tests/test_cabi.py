@@ -60,13 +60,13 @@ def test_no_cpu_fallback(engine_lib):
 
 
 def test_product_does_not_import_the_oracle():
-    """oracle/ is test infrastructure: nothing under spinwalk_b200/ may reference it."""
-    pkg = os.path.join(ROOT, "spinwalk_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
-                txt = open(os.path.join(dirpath, f)).read()
-                assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt and "import oracle" not in txt, f
+    """oracle/ is test infrastructure: nothing under spinwalk_b200/, host/ or include/ may reference it."""
+    for pkg in ("spinwalk_b200", "host", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt and "import oracle" not in txt, f
 
 
 def test_swk_prepare_matches_oracle(engine_lib, oracle):
