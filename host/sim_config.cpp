@@ -203,6 +203,7 @@ bool SimConfig::check(bool check_files)
     if (!strictly_ascending(dephasing_us)) return fail("Dephasing Times must be in ascending order and must not have duplicates values: " + join(dephasing_us));
     if (!strictly_ascending(gradient_us)) return fail("Gradient times must be in a strickly ascending order and must not have duplicates values: " + join(gradient_us));
     if (TR_us < 0 || timestep_us < 0) return fail("TR and timestep must be set");
+    if (timestep_us == 0) return fail("TIME_STEP must not be 0"); // the reference divides by it in timing_scale() and dies with SIGFPE
     if (scale_type != 0 && scale_type != 1 && scale_type != 2) return fail("WHAT_TO_SCALE must be 0, 1, or 2, but is " + std::to_string(scale_type));
     return true;
 }

@@ -101,3 +101,48 @@ def test_missing_files_and_output_dir(staged, tmp_path):
     assert r["scales"] == [0.125] and r["n_substrate"] == 3 and r["scale_type"] == 1
     r = ours(os.path.join(staged, "cfg", "nonexistent.ini"))
     assert not r["ok"] and "does not exist" in r["error"]
+
+
+# ---- randomised configs against the reference reader (hypothesis) ---------------------------------------------------
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+_num = st.one_of(st.integers(0, 200000).map(str), st.floats(0, 1e5, allow_nan=False).map(lambda v: f"{v:.4g}"),
+                 st.sampled_from(["1e3", "2.5e4", "100e3", "7", "0", "0.0", "50", "1e-9", "-1", "-3.5", "abc", "", "12 ; c", " 9 "]))
+_vec = st.lists(_num, min_size=0, max_size=4).map(" ".join)
+_scan_keys = ["TR", "TE", "RF_FA", "RF_PH", "RF_T", "DEPHASING", "DEPHASING_T", "GRADIENT_X", "GRADIENT_Y", "GRADIENT_Z", "GRADIENT_T",
+              "TIME_STEP", "DUMMY_SCAN", "LINEAR_PHASE_CYCLING", "QUADRATIC_PHASE_CYCLING"]
+_sim_keys = ["B0", "SEED", "NUMBER_OF_SPINS", "CROSS_FOV", "RECORD_TRAJECTORY", "MAX_ITERATIONS", "WHAT_TO_SCALE", "SCALE[0]", "SCALE[1]", "SCALE[3]"]
+_tis_keys = ["DIFFUSIVITY[0]", "DIFFUSIVITY[1]", "T1[0]", "T1[1]", "T2[0]", "T2[1]", "P_XY[0]", "P_XY[1]"]
+
+
+@st.composite
+def _child_ini(draw):
+    lines = ["[GENERAL]", "PARENT_CONFIG = base.ini"]
+    if draw(st.booleans()):
+        lines.append("SEQ_NAME = " + draw(st.sampled_from(["x", "a b", "q;r", ""])))
+    for sec, keys, strat in (("SCAN_PARAMETERS", _scan_keys, _vec), ("SIMULATION_PARAMETERS", _sim_keys, _num), ("TISSUE_PARAMETERS", _tis_keys, _vec)):
+        chosen = draw(st.lists(st.sampled_from(keys), max_size=5, unique=True))
+        if chosen:
+            lines.append(f"[{sec}]" + draw(st.sampled_from(["", " ; note", "   "])))
+            for k in chosen:
+                lines.append(draw(st.sampled_from(["", "  ", "\t"])) + k + draw(st.sampled_from(["=", " = ", " =", "= "])) + draw(strat))
+    return "\n".join(lines) + "\n"
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(text=_child_ini())
+def test_random_children_match_reference(staged, text):
+    """random child configs over base.ini: accepted or rejected alike, and when accepted, identical values.  (A malformed number
+    makes the reference throw from std::stof / stoi — it would terminate; both report failure here.)"""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/ref_config not built (needs /root/reference)")
+    p = os.path.join(staged, "cfg", "_random_child.ini")
+    with open(p, "w") as f:
+        f.write(text)
+    r = subprocess.run([REF_BIN, p], capture_output=True, text=True)
+    ref = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else {"ok": False}  # e.g. SIGFPE on TIME_STEP = 0
+    got = ours(p)
+    assert got["ok"] == ref["ok"], (text, got.get("error"))
+    if ref["ok"]:
+        assert strip(got) == strip(ref), text
