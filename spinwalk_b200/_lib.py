@@ -1,4 +1,4 @@
-"""ctypes declarations of include/spinwalk_engine.h (the C-ABI).  No torch, no numpy types cross it."""
+"""ctypes declarations of include/spinwalk_engine.h and include/spinwalk_phantom.h (the C-ABI).  No torch, no numpy types cross it."""
 from __future__ import annotations
 
 import ctypes as C
@@ -47,7 +47,27 @@ class Stats(C.Structure):  # struct swk_stats
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
-# every symbol include/spinwalk_engine.h declares: name -> (restype, argtypes)
+SHAPE_CYLINDER, SHAPE_SPHERE, SHAPE_TWOPOOLS = 0, 1, 2
+
+
+class PhantomSpec(C.Structure):  # struct swk_phantom_spec
+    _fields_ = [
+        ("shape", C.c_int32), ("fov_um", C.c_float), ("resolution", C.c_uint64), ("dchi", C.c_float), ("oxy_level", C.c_float),
+        ("radius_um", C.c_float), ("volume_fraction", C.c_float), ("orientation_deg", C.c_float), ("seed", C.c_int32),
+    ]
+
+
+class PhantomStats(C.Structure):  # struct swk_phantom_stats
+    _fields_ = [
+        ("n_shapes", C.c_uint32), ("volume_fraction", C.c_float), ("place_ms", C.c_float), ("kernel_ms", C.c_float),
+        ("n_launches", C.c_uint32), ("exact_columns", C.c_uint64),
+    ]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/spinwalk_engine.h and include/spinwalk_phantom.h declare: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
     "swk_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
@@ -71,6 +91,12 @@ SYMBOLS = {
     "swk_stream": (_P, [_P]),
     "swk_device_sums": (_P, [_P]),
     "swk_device_bytes": (C.c_uint64, [_P]),
+    # include/spinwalk_phantom.h
+    "swk_phantom_shapes": (C.c_int, [C.POINTER(PhantomSpec), _P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "swk_phantom_generate": (C.c_int, [C.c_int, C.POINTER(PhantomSpec), _P, _P, C.c_int, C.POINTER(PhantomStats)]),
+    "swk_generate_phantom": (C.c_int, [_P, C.POINTER(PhantomSpec), C.POINTER(PhantomStats)]),
+    "swk_get_phantom": (C.c_int, [_P, _P, _P]),
+    "swk_phantom_last_error": (C.c_char_p, []),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ OUT = os.path.join(HERE, "libspinwalk_b200.so")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
 ]
 
 

@@ -925,3 +925,147 @@ uint64_t swk_device_bytes(const swk_engine *e)
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Phantom generator (include/spinwalk_phantom.h)
+// ------------------------------------------------------------------------------------------------------------------------
+#include "phantom.cuh"
+
+namespace {
+thread_local std::string g_phantom_error;
+int phantom_fail(int code, const std::string &msg)
+{
+    g_phantom_error = msg;
+    return code;
+}
+void fill_stats(swk_phantom_stats *st, const swk_phantom_spec &sp, const std::vector<swk::phantom::Shape> &shapes, float place_ms, const swk::phantom::FillResult &fr)
+{
+    if (!st) return;
+    const double V = double(sp.resolution) * sp.resolution * sp.resolution;
+    st->n_shapes = uint32_t(shapes.size());
+    st->volume_fraction = float(double(fr.ones) * 100.0 / V); // ≙ accumulate(mask) * 100.0 / size (phantom_cylinder.cpp:270)
+    st->place_ms = place_ms;
+    st->kernel_ms = fr.kernel_ms;
+    st->n_launches = fr.n_launches;
+    st->exact_columns = fr.exact_columns;
+}
+} // namespace
+
+extern "C" {
+
+const char *swk_phantom_last_error(void) { return g_phantom_error.c_str(); }
+
+int swk_phantom_shapes(const swk_phantom_spec *spec, float *shapes, uint32_t cap, uint32_t *n_shapes)
+{
+    if (!spec || !n_shapes) return phantom_fail(SWK_ERR_INVALID, "swk_phantom_shapes: spec and n_shapes are mandatory");
+    std::vector<swk::phantom::Shape> placed;
+    float ms = 0.f;
+    std::string err;
+    const int rc = swk::phantom::place(*spec, placed, ms, err);
+    if (rc != SWK_OK) return phantom_fail(rc, err);
+    *n_shapes = uint32_t(placed.size());
+    for (size_t i = 0; shapes && i < placed.size() && i < cap; i++) {
+        shapes[4 * i + 0] = placed[i].x;
+        shapes[4 * i + 1] = placed[i].y;
+        shapes[4 * i + 2] = placed[i].z;
+        shapes[4 * i + 3] = placed[i].r;
+    }
+    return SWK_OK;
+}
+
+int swk_phantom_generate(int device, const swk_phantom_spec *spec, uint8_t *mask, float *fieldmap_T, int on_device, swk_phantom_stats *stats)
+{
+    if (!spec || !mask) return phantom_fail(SWK_ERR_INVALID, "swk_phantom_generate: spec and mask are mandatory");
+    const bool calc = swk::phantom::wants_fieldmap(*spec);
+    if (calc && !fieldmap_T) return phantom_fail(SWK_ERR_INVALID, "swk_phantom_generate: oxy_level >= 0 needs a fieldmap buffer");
+    std::vector<swk::phantom::Shape> placed;
+    float place_ms = 0.f;
+    std::string err;
+    int rc = swk::phantom::place(*spec, placed, place_ms, err);
+    if (rc != SWK_OK) return phantom_fail(rc, err);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev)
+        return phantom_fail(SWK_ERR_CUDA, "swk_phantom_generate: no usable CUDA device (this library has no CPU path for the voxel fill)");
+    if (cudaSetDevice(device) != cudaSuccess) return phantom_fail(SWK_ERR_CUDA, "cudaSetDevice failed");
+    int sm = 0;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    const size_t V = size_t(spec->resolution) * spec->resolution * spec->resolution;
+    uint8_t *d_mask = mask;
+    float *d_field = calc ? fieldmap_T : nullptr;
+    if (!on_device) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (V * (calc ? 5 : 1) > free_b) return phantom_fail(SWK_ERR_MEMORY, "swk_phantom_generate: phantom does not fit in free device memory");
+        d_mask = nullptr;
+        d_field = nullptr;
+        if (cudaMalloc(&d_mask, V) != cudaSuccess || (calc && cudaMalloc(&d_field, V * sizeof(float)) != cudaSuccess)) {
+            if (d_mask) cudaFree(d_mask);
+            return phantom_fail(SWK_ERR_MEMORY, "swk_phantom_generate: cudaMalloc failed");
+        }
+    } else if ((reinterpret_cast<uintptr_t>(mask) & 15) || (calc && (reinterpret_cast<uintptr_t>(fieldmap_T) & 15)))
+        return phantom_fail(SWK_ERR_INVALID, "swk_phantom_generate: device buffers must be 16-byte aligned");
+    swk::phantom::FillResult fr;
+    rc = swk::phantom::fill_device(*spec, placed, d_mask, d_field, nullptr, sm, fr);
+    if (rc == SWK_OK && !on_device) {
+        if (cudaMemcpy(mask, d_mask, V, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            (calc && cudaMemcpy(fieldmap_T, d_field, V * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)) {
+            rc = SWK_ERR_CUDA;
+            fr.error = "device-to-host copy of the phantom failed";
+        }
+    }
+    if (!on_device) {
+        cudaFree(d_mask);
+        if (d_field) cudaFree(d_field);
+    }
+    if (rc != SWK_OK) return phantom_fail(rc, fr.error);
+    fill_stats(stats, *spec, placed, place_ms, fr);
+    return SWK_OK;
+}
+
+int swk_generate_phantom(swk_engine *e, const swk_phantom_spec *spec, swk_phantom_stats *stats)
+{
+    if (!e) return SWK_ERR_INVALID;
+    if (!spec) return fail(e, SWK_ERR_INVALID, "swk_generate_phantom: spec is NULL");
+    std::vector<swk::phantom::Shape> placed;
+    float place_ms = 0.f;
+    std::string err;
+    int rc = swk::phantom::place(*spec, placed, place_ms, err);
+    if (rc != SWK_OK) return fail(e, rc, "swk_generate_phantom: " + err);
+    CK(cudaSetDevice(e->device));
+    const bool calc = swk::phantom::wants_fieldmap(*spec);
+    const size_t V = size_t(spec->resolution) * spec->resolution * spec->resolution;
+    e->has_phantom = false;
+    e->order_valid = false;
+    release(e->mask);
+    release(e->fieldmap);
+    release(e->packed);
+    e->packed_valid = false;
+    if ((rc = ensure(e, e->mask, V)) != SWK_OK) return rc;
+    if (calc && (rc = ensure(e, e->fieldmap, V * sizeof(float))) != SWK_OK) return rc;
+    swk::phantom::FillResult fr;
+    rc = swk::phantom::fill_device(*spec, placed, static_cast<uint8_t *>(e->mask.p), calc ? static_cast<float *>(e->fieldmap.p) : nullptr, e->stream, e->sm_count, fr);
+    if (rc != SWK_OK) return fail(e, rc, "swk_generate_phantom: " + fr.error);
+    e->mask_substrates = fr.ones ? 2 : 1; // max(mask) + 1 (monte_carlo.cu:113)
+    const float fov_m = spec->fov_um * 1e-6f; // phantom_base.cpp:63
+    for (int i = 0; i < 3; i++) { e->dims[i] = spec->resolution; e->fov[i] = fov_m; }
+    e->has_phantom = true;
+    fill_stats(stats, *spec, placed, place_ms, fr);
+    return SWK_OK;
+}
+
+int swk_get_phantom(swk_engine *e, uint8_t *mask, float *fieldmap_T)
+{
+    if (!e) return SWK_ERR_INVALID;
+    if (!e->has_phantom) return fail(e, SWK_ERR_STATE, "swk_get_phantom: no phantom");
+    CK(cudaSetDevice(e->device));
+    const size_t V = size_t(e->dims[0]) * e->dims[1] * e->dims[2];
+    if (mask) CK(cudaMemcpyAsync(mask, e->mask.p, V, cudaMemcpyDeviceToHost, e->stream));
+    if (fieldmap_T) {
+        if (!e->fieldmap.p) return fail(e, SWK_ERR_STATE, "swk_get_phantom: the phantom has no field map");
+        CK(cudaMemcpyAsync(fieldmap_T, e->fieldmap.p, V * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    return SWK_OK;
+}
+
+} // extern "C"

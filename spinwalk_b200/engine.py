@@ -119,6 +119,26 @@ class Engine:
         if rc != L.SWK_OK:
             raise EngineError(rc, (self._lib.swk_last_error(self._h) or b"").decode())
 
+    # ---- phantom generated on the device (include/spinwalk_phantom.h) ------------------------
+    def generate_phantom(self, spec):
+        """spec: spinwalk_b200.phantom_gen.PhantomSpec.  The phantom is generated in the engine's own device memory and
+        becomes its current phantom; returns the generator's stats dict."""
+        cs = spec.c()
+        st = L.PhantomStats()
+        self._ck(self._lib.swk_generate_phantom(self._h, C.byref(cs), C.byref(st)))
+        n = int(spec.resolution)
+        self.dims = (n, n, n)
+        self.fov = (float(np.float32(spec.fov_um) * np.float32(1e-6)),) * 3
+        self.has_fieldmap = spec.has_fieldmap
+        return st.asdict()
+
+    def get_phantom(self):
+        """(mask uint8 [nx,ny,nz], fieldmap float32 or None) copied from the device."""
+        mask = np.empty(self.dims, np.uint8)
+        fm = np.empty(self.dims, np.float32) if self.has_fieldmap else None
+        self._ck(self._lib.swk_get_phantom(self._h, mask.ctypes.data, None if fm is None else fm.ctypes.data))
+        return mask, fm
+
     # ---- phantom -------------------------------------------------------------------------
     def set_phantom(self, mask, fieldmap_T, fov_m):
         """mask uint8 [nx,ny,nz], fieldmap float32 (Tesla at 1 T) or None, fov in metres.
@@ -143,6 +163,7 @@ class Engine:
             self._ck(self._lib.swk_set_phantom(self._h, m.ctypes.data, None if f is None else f.ctypes.data, dims, fov, 0))
         self.fov = tuple(float(np.float32(f)) for f in fov_m)
         self.dims = tuple(int(d) for d in mask.shape)
+        self.has_fieldmap = fieldmap_T is not None
 
     # ---- sequence ------------------------------------------------------------------------
     def set_sequence(self, cfg: SimConfig):

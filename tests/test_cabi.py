@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def header_functions():
-    src = open(os.path.join(ROOT, "include", "spinwalk_engine.h")).read()
+    src = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("spinwalk_engine.h", "spinwalk_phantom.h"))
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(swk_[a-z_0-9]+)\s*\(", src)))
 
@@ -41,12 +41,13 @@ def test_struct_sizes_match_the_header(engine_lib):
 
     from spinwalk_b200 import _lib
 
-    prog = '#include <stdio.h>\n#include "spinwalk_engine.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(swk_params), sizeof(swk_tables), sizeof(swk_stats));return 0;}\n'
+    prog = ('#include <stdio.h>\n#include "spinwalk_phantom.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(swk_params), sizeof(swk_tables), '
+            'sizeof(swk_stats), sizeof(swk_phantom_spec), sizeof(swk_phantom_stats));return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(prog)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
         out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()
-    assert [int(v) for v in out] == [C.sizeof(_lib.Params), C.sizeof(_lib.Tables), C.sizeof(_lib.Stats)]
+    assert [int(v) for v in out] == [C.sizeof(_lib.Params), C.sizeof(_lib.Tables), C.sizeof(_lib.Stats), C.sizeof(_lib.PhantomSpec), C.sizeof(_lib.PhantomStats)]
 
 
 def test_no_cpu_fallback(engine_lib):

@@ -1,0 +1,123 @@
+"""CPU tests of the phantom-generator oracle and of the product's host-side shape placement.
+
+* oracle/phantom_oracle.c is pinned bit-exactly on the golden vectors the UNMODIFIED reference generator produced
+  (tests/golden/phantom/*.npz, tests/golden/make_phantom_golden.py) and, when the reference tree is present, on the reference
+  library itself (oracle/_ref/libswref_gen.so).
+* swk_phantom_shapes (host-only entry point of libspinwalk_b200.so: sequential RNG placement, no CUDA) must reproduce the
+  shape lists bit by bit.  The voxel fill needs a GPU: tests/test_phantom_gpu.py.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from phantom_cases import CASES, TWOPOOLS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "phantom")
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def pp(oracle):  # the `oracle` fixture builds oracle/*.so (and oracle/_ref when /root/reference exists)
+    from oracle import pyphantom
+
+    return pyphantom
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_golden(pp, name):
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    ph = pp.oracle(**CASES[name])
+    assert np.array_equal(ph.shapes.view(np.uint32), gold["shapes"].view(np.uint32))
+    assert np.float32(ph.bvf) == gold["bvf"]
+    assert digest(ph.mask) == str(gold["mask_sha256"])
+    n = CASES[name]["resolution"]
+    assert np.array_equal(ph.mask[:, :, n // 2], gold["mask_slice"])
+    if "fieldmap_sha256" in gold:
+        assert np.array_equal(ph.fieldmap[:, :, n // 2].view(np.uint32), gold["fieldmap_slice"].view(np.uint32))
+        assert digest(ph.fieldmap) == str(gold["fieldmap_sha256"])
+    else:
+        assert ph.fieldmap is None
+
+
+@pytest.mark.parametrize("name", ["cyl_random_oblique", "cyl_mask_only", "sph_fixed", "twopools_odd"])
+def test_oracle_matches_reference_library(pp, name):
+    if not pp.have_ref():
+        pytest.skip("oracle/_ref/libswref_gen.so not built (no reference tree here)")
+    kw = dict(CASES[name])
+    if kw["shape"] != TWOPOOLS:
+        kw["seed"] = kw["seed"] + 100  # not the golden's seed: a fresh comparison
+    a, b = pp.reference(**kw), pp.oracle(**kw)
+    assert np.array_equal(a.shapes.view(np.uint32), b.shapes.view(np.uint32))
+    assert np.array_equal(a.mask, b.mask)
+    assert a.bvf == b.bvf
+    if a.fieldmap is not None:
+        assert np.array_equal(a.fieldmap.view(np.uint32), b.fieldmap.view(np.uint32))
+
+
+def test_oracle_z_window_equals_full_volume(pp):
+    for name in ("cyl_random_oblique", "sph_fixed", "twopools_odd"):
+        full = pp.oracle(**CASES[name])
+        win = pp.oracle(zwin=(7, 12), **CASES[name])
+        assert np.array_equal(full.mask[:, :, 7:12], win.mask)
+        if full.fieldmap is not None:
+            assert np.array_equal(full.fieldmap[:, :, 7:12].view(np.uint32), win.fieldmap.view(np.uint32))
+
+
+def test_oracle_refuses_oversized_radius(pp):
+    with pytest.raises(RuntimeError):
+        pp.oracle(shape=0, fov_um=10.0, resolution=8, radius_um=5.0)  # 2 r >= fov (phantom_cylinder.cpp:87)
+
+
+# ---- product: host-side placement through the C-ABI (no GPU needed) ----
+
+@pytest.mark.parametrize("name", sorted(n for n in CASES if CASES[n]["shape"] != TWOPOOLS))
+def test_product_placement_is_bit_identical(pp, engine_lib, name):
+    from spinwalk_b200 import phantom_gen as pg
+
+    kw = CASES[name]
+    spec = pg.PhantomSpec(shape=kw["shape"], fov_um=kw["fov_um"], resolution=kw["resolution"], oxy_level=kw.get("Y", 0.78),
+                          radius_um=kw["radius_um"], volume_fraction=kw["volume_fraction"], orientation_deg=kw.get("orientation_deg", 90.0), seed=kw["seed"])
+    got = pg.shapes(spec)
+    want = np.load(os.path.join(GOLD, name + ".npz"))["shapes"]
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_product_placement_full_size_recipes(pp, engine_lib):
+    """The BASELINE phantoms' shape lists (C2 600^3 cylinders, C3 400^3 spheres, C5 1000^3 cylinders) against the oracle."""
+    from spinwalk_b200 import phantom_gen as pg
+
+    for kw in (dict(shape=0, fov_um=600.0, resolution=600, radius_um=8.0, volume_fraction=4.0, Y=0.78, seed=0),
+               dict(shape=0, fov_um=1000.0, resolution=1000, radius_um=8.0, volume_fraction=4.0, Y=0.78, seed=0),
+               dict(shape=1, fov_um=400.0, resolution=400, radius_um=-20.0, volume_fraction=40.0, Y=-1.0, seed=0)):
+        spec = pg.PhantomSpec(shape=kw["shape"], fov_um=kw["fov_um"], resolution=kw["resolution"], oxy_level=kw["Y"], radius_um=kw["radius_um"],
+                              volume_fraction=kw["volume_fraction"], seed=kw["seed"])
+        got, want = pg.shapes(spec), pp.oracle_shapes(**kw)
+        assert len(got) == len(want) and len(got) > 50
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_product_placement_errors(engine_lib):
+    from spinwalk_b200 import phantom_gen as pg
+
+    with pytest.raises(pg.PhantomError, match="too large"):
+        pg.shapes(pg.PhantomSpec(shape=0, fov_um=10.0, resolution=8, radius_um=5.0, seed=1))
+    with pytest.raises(pg.PhantomError, match="FOV or resolution"):
+        pg.shapes(pg.PhantomSpec(shape=1, fov_um=0.0, resolution=8, radius_um=1.0, seed=1))
+    with pytest.raises(pg.PhantomError, match="shape"):
+        pg.shapes(pg.PhantomSpec(shape=7, fov_um=10.0, resolution=8, radius_um=1.0, seed=1))
+
+
+def test_voxel_fill_has_no_cpu_path(engine_lib):
+    from spinwalk_b200 import phantom_gen as pg
+
+    if engine_lib.swk_device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(pg.PhantomError, match="no usable CUDA device"):
+        pg.generate(pg.PhantomSpec(shape=2, fov_um=50.0, resolution=16))
