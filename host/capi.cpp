@@ -93,3 +93,56 @@ int swkh_h5_write(const char *path, int n, const char *const *names, const int *
 }
 
 } // extern "C"
+
+#include "generators.h"
+#include "ini_edit.h"
+
+extern "C" {
+
+// `spinwalk dwi` (host/generators.cpp): edits `config` in place.  0 ok, 1 failed (message in buf).
+int swkh_dwi(const double *b, uint32_t n_b, const float dir[3], uint32_t start_ms, uint32_t delta_ms, uint32_t DELTA_ms, const char *config, char *buf, size_t n)
+{
+    swk_host::DwiArgs a;
+    a.b_value.assign(b, b + n_b);
+    a.dir = {dir[0], dir[1], dir[2]};
+    a.start_ms = start_ms;
+    a.delta_ms = delta_ms;
+    a.DELTA_ms = DELTA_ms;
+    a.config = config;
+    std::string err;
+    const bool ok = swk_host::generate_dwi(a, err);
+    if (buf && n) copy_out(err, buf, n);
+    return ok ? 0 : 1;
+}
+
+// `spinwalk config`
+int swkh_config(const char *seq_name, uint32_t TE_us, uint32_t timestep_us, const char *const *phantoms, uint32_t n_phantoms, const char *output, char *buf, size_t n)
+{
+    swk_host::ConfigArgs a;
+    a.seq_name = seq_name;
+    a.TE_us = TE_us;
+    a.timestep_us = timestep_us;
+    for (uint32_t i = 0; i < n_phantoms; i++) a.phantoms.push_back(phantoms[i]);
+    a.output = output;
+    std::string err;
+    const bool ok = swk_host::generate_config(a, err);
+    if (buf && n) copy_out(err, buf, n);
+    return ok ? 0 : 1;
+}
+
+// IniDocument round trip for the writer tests: parse `path`, apply n edits, update the file in place (pretty or not).
+// ops[i]: 0 set(section,key,value), 1 remove key, 2 remove section, 3 touch section.
+int swkh_ini_edit(const char *path, int n, const int *ops, const char *const *sections, const char *const *keys, const char *const *values, int pretty)
+{
+    swk_host::IniDocument d;
+    d.load(path); // a missing file gives an empty document, update_file then creates it
+    for (int i = 0; i < n; i++) {
+        if (ops[i] == 0) d.set(sections[i], keys[i], values[i]);
+        else if (ops[i] == 1) d.remove(sections[i], keys[i]);
+        else if (ops[i] == 2) d.remove_section(sections[i]);
+        else d.touch_section(sections[i]);
+    }
+    return d.update_file(path, pretty != 0) ? 0 : 1;
+}
+
+} // extern "C"

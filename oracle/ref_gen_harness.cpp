@@ -23,6 +23,7 @@
 #undef protected
 #include "config/handler.h"
 #include "dwi/handler.h"
+#include "ini.h" // the reference's vendored mINI (include/ini.h), built with MINI_CASE_SENSITIVE like the reference (CMakeLists.txt:36)
 
 namespace {
 // the generators draw progress bars and banners on std::cout; keep the caller's stdout clean
@@ -112,6 +113,22 @@ int swref_config(const char *seq_name, uint32_t TE_us, uint32_t timestep_us, con
     for (uint32_t i = 0; i < n_phantoms; i++) a.phantoms.push_back(phantoms[i]);
     a.output = output;
     return config::handler::execute(a) ? 0 : 1;
+}
+
+// mINI itself: read `path`, apply n edits, INIFile::write(ini, pretty) — what src/dwi/pgse.cpp:93-95,145 does around its edits.
+// ops[i]: 0 ini[s][k] = v, 1 ini[s].remove(k), 2 ini.remove(s), 3 ini[s].
+int swref_ini_edit(const char *path, int n, const int *ops, const char *const *sections, const char *const *keys, const char *const *values, int pretty)
+{
+    mINI::INIFile file(path);
+    mINI::INIStructure ini;
+    file.read(ini);
+    for (int i = 0; i < n; i++) {
+        if (ops[i] == 0) ini[sections[i]][keys[i]] = values[i];
+        else if (ops[i] == 1) { if (ini.has(sections[i])) ini[sections[i]].remove(keys[i]); }
+        else if (ops[i] == 2) ini.remove(sections[i]);
+        else ini[sections[i]];
+    }
+    return file.write(ini, pretty != 0) ? 0 : 1;
 }
 
 } // extern "C"

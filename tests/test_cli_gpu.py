@@ -117,3 +117,85 @@ def test_cli_error_conventions(cli, tmp_path):
                                       .replace("P_XY[0] = 1.0 0.0\nP_XY[1] = 0.0 1.0", "P_XY[0] = 1.0"))
     r = subprocess.run([cli, "sim", "-c", str(tmp_path / "one.ini")], capture_output=True, text=True)
     assert r.returncode == 1 and "Simulation failed" in r.stderr and "substrate" in r.stderr  # monte_carlo.cu:113-118
+
+
+# ---- the generator subcommands: phantom (GPU voxel fill), config, dwi — and the whole reference workflow through the CLI ----
+
+def _sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_cli_phantom_files_hold_the_reference_generator_arrays(cli, tmp_path):
+    """`spinwalk phantom -c / -s / -t`: the phantom file carries the datasets of phantom_base::save (phantom_base.cpp:69-103) and the
+    mask / field map are, byte for byte, what the reference's generator makes (goldens: SHA-256 of its arrays)."""
+    from phantom_cases import CASES
+
+    gold_dir = os.path.join(h5util.ROOT, "tests", "golden", "phantom")
+    flags = {0: "-c", 1: "-s", 2: "-t"}
+    for name in ("cyl_bold", "cyl_mask_only", "sph_fixed", "twopools_odd"):
+        kw = CASES[name]
+        out = str(tmp_path / "made" / (name + ".h5"))  # the directory does not exist yet (phantom_base.cpp:72-80)
+        cmd = [cli, "phantom", flags[kw["shape"]], "-f", str(kw["fov_um"]), "-z", str(kw["resolution"]), "-o", out]
+        if kw["shape"] != 2:
+            cmd += ["-r", str(kw["radius_um"]), "-v", str(kw["volume_fraction"]), "-y", str(kw["Y"]), "-e", str(kw["seed"]), "-n", str(kw.get("orientation_deg", 90.0))]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "Done." in r.stdout
+        gold = np.load(os.path.join(gold_dir, name + ".npz"))
+        has_field = "fieldmap_sha256" in gold
+        assert sorted(h5util.names(out)) == sorted(["mask", "fov", "bvf"] + (["fieldmap"] if has_field else []))
+        n = kw["resolution"]
+        shape, dt, _ = h5util.info(out, "mask")
+        assert shape == (n, n, n) and np.dtype(dt) == np.uint8
+        assert _sha(h5util.read(out, "mask")) == str(gold["mask_sha256"])
+        if has_field:
+            shape, dt, _ = h5util.info(out, "fieldmap")
+            assert shape == (n, n, n) and np.dtype(dt) == np.float32
+            assert _sha(h5util.read(out, "fieldmap")) == str(gold["fieldmap_sha256"])
+        assert np.array_equal(h5util.read(out, "fov"), np.full(3, np.float32(kw["fov_um"]) * np.float32(1e-6), np.float32))
+        assert h5util.read(out, "bvf").ravel()[0] == gold["bvf"]
+
+
+def test_cli_phantom_refusals(cli, tmp_path):
+    out = str(tmp_path / "x.h5")
+    r = subprocess.run([cli, "phantom", "-c", "-f", "10", "-z", "8", "-r", "6", "-e", "1", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 1 and "Phantom generation failed" in r.stderr and "too large" in r.stderr  # phantom_cylinder.cpp:87-91
+    r = subprocess.run([cli, "phantom", "-c", "-z", "8", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 1 and "--fov is required" in r.stderr
+    r = subprocess.run([cli, "phantom", "-p", "-f", "10", "-z", "8", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 1 and "ply" in r.stderr
+    assert not os.path.exists(out)
+
+
+def test_cli_whole_workflow_config_phantom_dwi_sim(cli, tmp_path):
+    """The demo notebooks' chain, every step through this CLI: phantom -> config -> dwi -> sim.  Free diffusion (P_XY = 1 everywhere,
+    no relaxation) must give the Stejskal-Tanner answer exp(-b D) per b-value (demo/spinwalk_dwi.ipynb)."""
+    ph = str(tmp_path / "phantoms" / "spheres.h5")
+    r = subprocess.run([cli, "phantom", "-s", "-r", "-6", "-v", "20", "-f", "60", "-z", "48", "-y", "-1", "-e", "9", "-o", ph, "-q"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cfg = str(tmp_path / "cfg" / "pgse.ini")
+    r = subprocess.run([cli, "config", "-s", "GRE", "-p", ph, "-e", "40000", "-t", "50", "-o", cfg], capture_output=True, text=True)
+    assert r.returncode == 0 and "Configuration file is generated in" in r.stdout, r.stderr
+    b = [200, 1000, 3000]
+    r = subprocess.run([cli, "dwi", "-b", *map(str, b), "-v", "1", "0", "0", "-d", "5", "10", "20", "-c", cfg], capture_output=True, text=True)
+    assert r.returncode == 0 and "generated successfully" in r.stdout, r.stderr
+    # the notebook then edits the tissue parameters by hand: free diffusion, no relaxation, a fixed seed, more spins
+    default = str(tmp_path / "cfg" / "default_config.ini")
+    txt = open(default).read()
+    for old, new in (("P_XY[0] = 1.0 0.0", "P_XY[0] = 1.0 1.0"), ("P_XY[1] = 0.0 1.0", "P_XY[1] = 1.0 1.0"), ("T1[0] = 2200", "T1[0] = -1"), ("T1[1] = 2200", "T1[1] = -1"),
+                     ("T2[0] = 41", "T2[0] = -1"), ("T2[1] = 41", "T2[1] = -1"), ("SEED = 0", "SEED = 7"), ("NUMBER_OF_SPINS = 1e5", "NUMBER_OF_SPINS = 40000"),
+                     ("CROSS_FOV = 0", "CROSS_FOV = 1")):
+        assert old in txt
+        txt = txt.replace(old, new)
+    open(default, "w").write(txt)
+    r = subprocess.run([cli, "sim", "-c", cfg, "-q"], capture_output=True, text=True, cwd=str(tmp_path / "cfg"))
+    assert r.returncode == 0, r.stderr
+    out = str(tmp_path / "cfg" / "outputs" / "gre_spheres.h5")  # {OUTPUT_DIR}/{SEQ_NAME}_{phantom stem}.h5 (config_reader.cpp:266-271)
+    M = h5util.read(out, "M")
+    assert M.shape == (3, 40000, 1, 3)
+    sig = np.hypot(M[..., 0].mean(axis=1), M[..., 1].mean(axis=1)).ravel()
+    want = np.exp(-np.asarray(b, np.float64) * 1e6 * 1.0e-9)  # b in s/mm^2 -> s/m^2, D = 1e-9 m^2/s
+    # Monte-Carlo standard error of |<exp(i phi)>| with 4e4 spins is <= 0.005; the reference's discrete gradient samples add ~1 % in b
+    assert np.all(np.abs(sig - want) < 0.02 + 0.03 * want), (sig, want)
