@@ -2,6 +2,7 @@
 """bench.py — spin-steps/s of the `sim` hot path on B200.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c3r|c4|c5]
+  python bench.py --workload ph-c2|ph-c5|ph-c3 ...     the phantom generator on the same recipes: voxels/s
 
 A "step" is one pass of the hot path over the whole workload: all spins x all scales x all
 timepoints of one phantom (what one iteration of the reference's phantom loop does,
@@ -226,6 +227,123 @@ def reference_cuda(cfg_kw, ph, mask2, fm2, fov, device, target_s=10.0):
             "sample": f"first {n_spins} spins x all {len(cfg_kw['scales'])} scales of the workload ({steps:.3g} spin-steps, {sec:.2f} s of kernel time)"}
 
 
+PHANTOM_RECIPES = {  # `spinwalk phantom` invocations behind the BASELINE configs
+    "ph-c2": (dict(shape=0, fov_um=600.0, resolution=600, radius_um=8.0, volume_fraction=4.0, Y=0.78, orientation_deg=90.0, seed=0),
+              "phantom -c -r 8 -v 4 -y 0.78 -n 90 -f 600 -z 600 -e 0 (C2's 600^3 vessel phantom: mask + field map)"),
+    "ph-c5": (dict(shape=0, fov_um=1000.0, resolution=1000, radius_um=8.0, volume_fraction=4.0, Y=0.78, orientation_deg=90.0, seed=0),
+              "phantom -c -r 8 -v 4 -y 0.78 -n 90 -f 1000 -z 1000 -e 0 (C5's 1000^3 vessel phantom: mask + field map, 5 GB)"),
+    "ph-c3": (dict(shape=1, fov_um=400.0, resolution=400, radius_um=-20.0, volume_fraction=40.0, Y=-1.0, seed=0),
+              "phantom -s -r -20 -v 40 -y -1 -f 400 -z 400 -e 0 (C3's 400^3 permeable-sphere phantom: mask only, 44k spheres)"),
+    "ph-s256": (dict(shape=1, fov_um=256.0, resolution=256, radius_um=-20.0, volume_fraction=30.0, Y=0.78, seed=0),
+                "phantom -s -r -20 -v 30 -y 0.78 -f 256 -z 256 -e 0 (spheres with dipole field map)"),
+}
+
+
+def phantom_bench(args):
+    """The phantom generator on one GPU: `value` = voxels/s of the device voxel fill into device-resident buffers (CUDA events),
+    `e2e` = swk_phantom_generate with HOST buffers (placement + fill + D2H), `cpu_baseline` = the reference's own generator classes
+    (oracle/_ref/libswref_gen_omp.so: unmodified src/phantom/*.cpp with OpenMP, all host cores) on the same recipe."""
+    kw, desc = PHANTOM_RECIPES[args.workload]
+    n = kw["resolution"]
+    V = n ** 3
+    if args.impl == "reference":
+        from oracle import pyphantom as pp
+
+        if int(os.environ.get("RANK", 0)) != 0:
+            return
+        ts = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pp.reference(omp=pp.have_ref(omp=True), **kw)
+            if i >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+        v = V * len(ts) / sum(ts)
+        print(json.dumps({"impl": "reference", "metric": "voxels/s", "value": v, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+                          "data": "synthetic", "config": {"workload": desc}, "gpu_launches": 0,
+                          "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "reference", "sample": "the whole phantom"},
+                          "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+
+    from spinwalk_b200 import phantom_gen as pg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the phantom generator has no CPU path for the voxel fill")
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    spec = pg.PhantomSpec(shape=kw["shape"], fov_um=kw["fov_um"], resolution=n, oxy_level=kw["Y"], radius_um=kw["radius_um"], volume_fraction=kw["volume_fraction"],
+                          orientation_deg=kw.get("orientation_deg", 90.0), seed=kw["seed"])
+    mask_d = torch.empty((n, n, n), dtype=torch.uint8, device=dev)
+    fm_d = torch.empty((n, n, n), dtype=torch.float32, device=dev) if spec.has_fieldmap else None
+    out_bytes = V * (5 if spec.has_fieldmap else 1)
+    for _ in range(args.warmup):
+        pg.generate(spec, out=(mask_d, fm_d))
+    ker_ms, place_ms, launches = 0.0, 0.0, 0
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _, _, _, st = pg.generate(spec, out=(mask_d, fm_d))
+            ker_ms += st["kernel_ms"]
+            place_ms += st["place_ms"]
+            launches += st["n_launches"]
+        torch.cuda.synchronize(dev)
+        wall_s = time.perf_counter() - t0
+    clocks = clk.summary()
+    del mask_d, fm_d
+    torch.cuda.empty_cache()
+    # e2e: the call `spinwalk phantom` makes — host buffers out (allocated and touched once, like the caller's std::vector)
+    host = (np.zeros((n, n, n), np.uint8), np.zeros((n, n, n), np.float32) if spec.has_fieldmap else None)
+    pg.generate(spec, device=local_rank, out_host=host)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pg.generate(spec, device=local_rank, out_host=host)
+    e2e_s = time.perf_counter() - t0
+    del host
+    peak, peak_src = measured_peaks()
+    achieved = out_bytes / (ker_ms / args.steps * 1e-3) / 1e9
+    line = {"metric": "voxels/s", "value": V * args.steps / (ker_ms * 1e-3), "unit": "voxels/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ker_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": desc, "voxels": V, "shapes": st["n_shapes"], "volume_fraction_pct": st["volume_fraction"], "placement_ms_host": place_ms / args.steps,
+                       "exact_columns": st["exact_columns"], "l2": "outputs larger than L2 are rewritten every pass" if out_bytes > 126e6 else "output fits in L2"},
+            "clocks": clocks, "wall_ms_per_step": 1e3 * wall_s / args.steps, "gpu_launches": launches,
+            "e2e": {"value": V * args.steps / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": out_bytes, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "api": "swk_phantom_generate (C-ABI) with pageable host buffers: placement + voxel fill + D2H of mask and field map"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "swk::phantom::slab_broadcast_kernel" if kw["shape"] == 0 else "swk::phantom::sphere_fill_kernel",
+                         "algorithmic_bytes_per_launch": out_bytes, "kernel_ms_per_launch": ker_ms / args.steps,
+                         "note": "5 B written per voxel (1 B mask + 4 B field) or 1 B without field map; the sphere kernel is bound by two IEEE double "
+                                 "divisions per (voxel, sphere) pair, not by HBM"}}
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import pyphantom as pp
+
+            have_omp = pp.have_ref(omp=True)
+            if have_omp or pp.have_ref():
+                # bounded sample: at most 600^3 voxels at the recipe's voxel size (the reference needs 12 B of host grid per voxel and minutes beyond that)
+                nc = min(n, 600)
+                kw_cpu = dict(kw, resolution=nc, fov_um=kw["fov_um"] * nc / n)
+                t0 = time.perf_counter()
+                pp.reference(omp=have_omp, **kw_cpu)
+                sec = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": nc ** 3 / sec, "unit": "voxels/s", "cores": os.cpu_count() if have_omp else 1, "kind": "reference",
+                                        "sample": f"{'the whole phantom' if nc == n else f'the same recipe at {nc}^3 voxels'} once with the reference's generator classes "
+                                                  f"({'OpenMP' if have_omp else 'serial'} build): {sec:.1f} s"}
+            else:
+                import subprocess as sp
+
+                sp.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True)
+                zw = (0, max(1, n // 16))
+                t0 = time.perf_counter()
+                pp.oracle(zwin=zw, **kw)
+                sec = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": n * n * zw[1] / sec, "unit": "voxels/s", "cores": 1, "kind": "port", "sample": f"z slices [0, {zw[1]}) of the phantom: {sec:.1f} s"}
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -239,6 +357,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    if args.workload in PHANTOM_RECIPES:
+        return phantom_bench(args)
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

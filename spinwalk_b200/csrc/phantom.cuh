@@ -51,13 +51,61 @@ inline std::vector<float> voxel_centres(float fov, size_t res)
     return g;
 }
 
+// Uniform grid over the shape centres for the collision test.  The reference scans every placed shape for every candidate
+// (O(N) per candidate, 44 k spheres for the C3 phantom); here only the shapes of nearby cells are visited — in their ORIGINAL
+// index order, because with random radii the candidate shrinks step by step and the outcome depends on the visiting order.
+// Why the others cannot matter: a placed shape (radius R <= rmax) interacts with a candidate (radius r <= rmax) only when
+// dist <= R, dist <= r or dist < fl(R + r), i.e. dist <= 2 rmax (+ rounding); cells are 1.0001 rmax wide (or wider when that
+// would give too many cells) and the query takes 2 cells either side, so a shape outside the query is > 2.0002 rmax away along an axis.
+template <int DIM>
+class CentreGrid {
+public:
+    CentreGrid(double lo, double hi, double rmax)
+    {
+        origin_ = lo;
+        cell_ = std::max(rmax * 1.0001, (hi - lo) / (DIM == 2 ? 1024.0 : 192.0));
+        if (!(cell_ > 0)) cell_ = 1.0;
+        n_ = int(std::floor((hi - lo) / cell_)) + 1;
+        cells_.resize(DIM == 2 ? size_t(n_) * n_ : size_t(n_) * n_ * n_);
+    }
+    void add(uint32_t index, const float *c) { cells_[flat(cell_of(c[0]), cell_of(c[1]), DIM == 3 ? cell_of(c[2]) : 0)].push_back(index); }
+    // calls visit(index) for every shape within 2 cells of c (any order)
+    template <class F>
+    void for_nearby(const float *c, F visit) const
+    {
+        const int cx = cell_of(c[0]), cy = cell_of(c[1]), cz = DIM == 3 ? cell_of(c[2]) : 0;
+        const int z0 = DIM == 3 ? std::max(0, cz - 2) : 0, z1 = DIM == 3 ? std::min(n_ - 1, cz + 2) : 0;
+        for (int x = std::max(0, cx - 2); x <= std::min(n_ - 1, cx + 2); x++)
+            for (int y = std::max(0, cy - 2); y <= std::min(n_ - 1, cy + 2); y++)
+                for (int z = z0; z <= z1; z++)
+                    for (const uint32_t i : cells_[flat(x, y, z)]) visit(i);
+    }
+
+private:
+    int cell_of(float x) const { return std::min(n_ - 1, std::max(0, int(std::floor((double(x) - origin_) / cell_)))); }
+    size_t flat(int x, int y, int z) const { return DIM == 2 ? size_t(x) * n_ + y : (size_t(x) * n_ + y) * n_ + z; }
+    double origin_, cell_;
+    int n_;
+    std::vector<std::vector<uint32_t>> cells_;
+};
+
 // Does candidate c (radius may shrink when radii are random) collide with the shapes placed so far?
 // DIM = 2: distance in the xy plane (parallel cylinders, phantom_cylinder.cpp:22-56); DIM = 3: spheres (phantom_sphere.cpp:23-55).
-// Serial visiting order (the OpenMP build of the reference races on `radius`: the result then depends on thread timing).
+// The reference visits ALL placed shapes in index order (serially; its OpenMP build races on `radius`, the result then depends
+// on thread timing).  The same outcome with far fewer visits:
+//   1. a shape can only take part while dist <= R, dist <= r or dist < fl(R + r) for the candidate's current radius r, and r
+//      never grows beyond its initial value r0 (up to a rounding of fl(dist - R)), so shapes with dist > R + r0 + margin are
+//      skipped — `dist` being the reference's own float expression;
+//   2. the survivors (a handful) are sorted by index and taken through the reference's sequential rule.
 template <int DIM>
-inline bool collides(const std::vector<Shape> &placed, const float *c, float &radius, bool random_radius)
+inline bool collides(const std::vector<Shape> &placed, const CentreGrid<DIM> &grid, std::vector<std::pair<uint32_t, float>> &scratch, const float *c,
+                     float &radius, bool random_radius)
 {
-    for (const Shape &s : placed) {
+    scratch.clear();
+    const float reach = radius * 1.001f + 1e-4f;
+    bool inside_one = false; // centre inside a placed shape: rejected whatever the order
+    grid.for_nearby(c, [&](uint32_t i) {
+        const Shape &s = placed[i];
         const float d0 = c[0] - s.x, d1 = c[1] - s.y;
         float dist;
         if (DIM == 2) dist = std::sqrt(d0 * d0 + d1 * d1);
@@ -65,10 +113,17 @@ inline bool collides(const std::vector<Shape> &placed, const float *c, float &ra
             const float d2 = c[2] - s.z;
             dist = std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
         }
-        if (dist <= s.r || dist <= radius) return true;
-        if (dist < s.r + radius) {
+        if (dist <= s.r) inside_one = true;
+        else if (dist <= s.r + reach) scratch.emplace_back(i, dist);
+    });
+    if (inside_one) return true;
+    std::sort(scratch.begin(), scratch.end());
+    for (const auto &[i, dist] : scratch) {
+        const float R = placed[i].r;
+        if (dist <= radius) return true;
+        if (dist < R + radius) {
             if (!random_radius) return true;
-            radius = dist - s.r;
+            radius = dist - R;
         }
     }
     return false;
@@ -117,18 +172,21 @@ inline int place_cylinders(const swk_phantom_spec &sp, const std::vector<float> 
     std::uniform_real_distribution<float> u01(0.f, 1.f);
     float filled = 0, whole = fov * fov * fov;
     out.clear();
+    CentreGrid<2> grid(-double(rmax), double(fov) + rmax, rmax); // centres lie in [-r, fov + r]
+    std::vector<std::pair<uint32_t, float>> near;
     uint64_t rejected = 0;
     for (int32_t percent = 0; percent < 100;) {
         if (rejected++ > kMaxConsecutiveRejections) return SWK_PLACE_STALLED;
         float rad = random_radius ? u01(gen) * rmax : rmax;
         float c[3];
         for (float &v : c) v = u01(gen) * (fov + 2 * rad) - rad;
-        if (collides<2>(out, c, rad, random_radius)) continue;
+        if (collides<2>(out, grid, near, c, rad, random_radius)) continue;
         const float vol = cylinder_volume(g, fov, sp.resolution, c, rad);
         if (100 * (vol + filled) / whole > 1.02 * vf || vol < 0) continue;
         rejected = 0;
         filled += vol;
         percent = int32_t(100 * (100. * filled / whole / vf));
+        grid.add(uint32_t(out.size()), c);
         out.push_back({c[0], c[1], c[2], rad});
     }
     return SWK_OK;
@@ -145,15 +203,18 @@ inline int place_spheres(const swk_phantom_spec &sp, std::vector<Shape> &out)
     std::uniform_real_distribution<float> u01(0.f, 1.f);
     float filled = 0, whole = fov * fov * fov;
     out.clear();
+    CentreGrid<3> grid(0.0, double(fov), rmax); // centres lie in [0, fov)
+    std::vector<std::pair<uint32_t, float>> near;
     uint64_t rejected = 0;
     for (int32_t percent = 0; percent < 100;) {
         if (rejected++ > kMaxConsecutiveRejections) return SWK_PLACE_STALLED;
         float rad = random_radius ? u01(gen) * rmax : rmax;
         float c[3];
         for (float &v : c) v = u01(gen) * fov;
-        if (collides<3>(out, c, rad, random_radius)) continue;
+        if (collides<3>(out, grid, near, c, rad, random_radius)) continue;
         rejected = 0;
         filled += 4 * M_PI / 3 * rad * rad * rad;
+        grid.add(uint32_t(out.size()), c);
         out.push_back({c[0], c[1], c[2], rad});
         percent = int32_t(0.95 * 100 * (100. * filled / whole / vf)); // 0.95: spheres cut by the FoV faces
     }
@@ -194,25 +255,49 @@ __device__ __forceinline__ double cyl_term(const CylConst &k, float p0, float p1
     return __dmul_rn(__dmul_rn(__dmul_rn(k.k_out, (double)__fdiv_rn(r2, d2)), (double)c2phi), (double)k.sin2);
 }
 
-// [res][res] slab: thread = (x, y) column, y fastest.  ones += number of masked columns.
+// [res][res] slab: thread = (x, y) column, y fastest; a block owns 256 consecutive columns and keeps only the cylinders whose
+// box meets them (order-preserving ballot compaction, as in sphere_fill_kernel).  counters[0] += number of masked columns.
 template <bool CALC>
 __global__ void __launch_bounds__(256) cyl_slab_kernel(const float *__restrict__ g, const CylDev *__restrict__ cyl, uint32_t n_cyl, uint32_t res,
                                                        CylConst k, uint8_t *__restrict__ mask2, float *__restrict__ field2,
                                                        uint32_t *__restrict__ exact_list, unsigned int *__restrict__ counters /*[0]=ones [1]=exact*/)
 {
     __shared__ CylDev s_cyl[256];
-    const uint32_t col = blockIdx.x * 256 + threadIdx.x;
-    const bool live = col < res * res;
+    __shared__ uint32_t s_warp_hits[8];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_cols = res * res;
+    const uint32_t first = blockIdx.x * 256, last = min(first + 255u, n_cols - 1);
+    const uint32_t col = first + threadIdx.x;
+    const bool live = col < n_cols;
     const int32_t px = live ? int32_t(col / res) : 0, py = live ? int32_t(col % res) : 0;
+    // the block's columns: x rows [bx0, bx1]; y range only when they share one row
+    const int32_t bx0 = int32_t(first / res), bx1 = int32_t(last / res);
+    const int32_t by0 = bx0 == bx1 ? int32_t(first % res) : 0, by1 = bx0 == bx1 ? int32_t(last % res) : int32_t(res) - 1;
     const float gx = g[px], gy = g[py];
     float f = 0.f;
     bool in_shape = false, exact = false;
     for (uint32_t base = 0; base < n_cyl; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        CylDev mine;
+        bool hit = false;
+        if (i < n_cyl) {
+            mine = cyl[i];
+            hit = mine.x0 <= bx1 && mine.x1 > bx0 && mine.y0 <= by1 && mine.y1 > by0;
+        }
+        const uint32_t vote = __ballot_sync(0xffffffffu, hit);
+        __syncthreads(); // previous batch fully consumed
+        if (lane == 0) s_warp_hits[warp] = __popc(vote);
         __syncthreads();
-        if (base + threadIdx.x < n_cyl) s_cyl[threadIdx.x] = cyl[base + threadIdx.x];
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < 8; w++) {
+            const uint32_t c = s_warp_hits[w];
+            before += w < warp ? c : 0;
+            total += c;
+        }
+        if (hit) s_cyl[before + __popc(vote & ((1u << lane) - 1u))] = mine;
         __syncthreads();
-        const uint32_t m = min(256u, n_cyl - base);
-        for (uint32_t j = 0; j < m; j++) {
+        for (uint32_t j = 0; j < total; j++) {
             const CylDev c = s_cyl[j];
             if (px < c.x0 || px >= c.x1 || py < c.y0 || py >= c.y1) continue;
             const float p0 = __fsub_rn(gx, c.cx), p1 = __fsub_rn(gy, c.cy);
@@ -237,42 +322,58 @@ __global__ void __launch_bounds__(256) cyl_slab_kernel(const float *__restrict__
 }
 
 // slab[col] -> volume[col*res + z] for all z.  A block streams 4096 consecutive voxels per iteration: one 16 B mask store
-// and four coalesced 16 B field stores per thread.  V % 16 voxels at the end are written one by one.
+// and four coalesced 16 B field stores per thread.  One 64-bit division per chunk; a store that lies inside one column (nearly
+// all of them) is a splat of one slab value, the others walk their 4 / 16 voxels.  V % 4096 voxels at the end go one by one.
 template <bool CALC>
 __global__ void __launch_bounds__(256) slab_broadcast_kernel(const uint8_t *__restrict__ mask2, const float *__restrict__ field2, uint32_t res, uint64_t V,
                                                              uint8_t *__restrict__ mask, float *__restrict__ field)
 {
     const uint64_t n_chunks = V / 4096;
     const uint32_t last_col = res * res - 1;
+    const uint32_t step_col = 1024u / res, step_z = 1024u % res; // a field store of the next round lies 1024 voxels further
     for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const uint64_t v0 = ch * 4096;
-        const uint64_t col0 = v0 / res;             // one 64-bit division per chunk; the rest is 32-bit
+        const uint64_t col0 = v0 / res;
         const uint32_t z0 = uint32_t(v0 - col0 * res);
         { // mask: voxels [v0 + 16 t, +16)
             const uint32_t off = z0 + 16u * threadIdx.x;
             uint32_t col = uint32_t(col0) + off / res, z = off % res;
-            uint32_t w[4] = {0, 0, 0, 0};
             uint32_t mv = mask2[min(col, last_col)];
+            uint4 w;
+            if (z + 16u <= res) w.x = w.y = w.z = w.w = mv * 0x01010101u;
+            else {
+                uint32_t b[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                w[i >> 2] |= mv << (8 * (i & 3));
-                if (++z == res) { z = 0; col++; mv = mask2[min(col, last_col)]; }
+                for (int i = 0; i < 16; i++) {
+                    b[i >> 2] |= mv << (8 * (i & 3));
+                    if (++z == res) { z = 0; col++; mv = mask2[min(col, last_col)]; }
+                }
+                w = make_uint4(b[0], b[1], b[2], b[3]);
             }
-            *reinterpret_cast<uint4 *>(mask + v0 + 16u * threadIdx.x) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(mask + v0 + 16u * threadIdx.x) = w;
         }
         if (CALC) {
+            const uint32_t off = z0 + 4u * threadIdx.x;
+            uint32_t col = uint32_t(col0) + off / res, z = off % res;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const uint32_t e = 4u * (q * 256 + threadIdx.x), off = z0 + e;
-                uint32_t col = uint32_t(col0) + off / res, z = off % res;
-                float o[4];
                 float fv = field2[min(col, last_col)];
+                float4 o;
+                if (z + 4u <= res) o = make_float4(fv, fv, fv, fv);
+                else {
+                    float t[4];
+                    uint32_t c2 = col, z2 = z;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    o[i] = fv;
-                    if (++z == res) { z = 0; col++; fv = field2[min(col, last_col)]; }
+                    for (int i = 0; i < 4; i++) {
+                        t[i] = fv;
+                        if (++z2 == res) { z2 = 0; c2++; fv = field2[min(c2, last_col)]; }
+                    }
+                    o = make_float4(t[0], t[1], t[2], t[3]);
                 }
-                *reinterpret_cast<float4 *>(field + v0 + e) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4 *>(field + v0 + 4u * (q * 256 + threadIdx.x)) = o;
+                col += step_col;
+                z += step_z;
+                if (z >= res) { z -= res; col++; }
             }
         }
     }

@@ -62,8 +62,10 @@ def shapes(spec: PhantomSpec) -> np.ndarray:
     return out
 
 
-def generate(spec: PhantomSpec, device: int = 0, out=None):
+def generate(spec: PhantomSpec, device: int = 0, out=None, out_host=None):
     """Returns (mask uint8 [n,n,n], fieldmap float32 [n,n,n] or None, fov_m float32[3], stats dict).
+
+    out_host = (mask, fieldmap) C-contiguous numpy arrays of those shapes / dtypes to fill instead of allocating new ones.
 
     out = (mask, fieldmap) torch CUDA tensors (uint8 / float32, contiguous, [n,n,n]) makes the generator write into them on the
     device instead of allocating numpy arrays (fieldmap may be None when the spec has no field map)."""
@@ -84,7 +86,15 @@ def generate(spec: PhantomSpec, device: int = 0, out=None):
         torch.cuda.synchronize(mask.device)
         _ck(lib, lib.swk_phantom_generate(mask.device.index or 0, C.byref(cs), mask.data_ptr(), fp, 1, C.byref(st)))
         return mask, (fm if spec.has_fieldmap else None), fov, st.asdict()
-    mask = np.empty((n, n, n), np.uint8)
-    fm = np.empty((n, n, n), np.float32) if spec.has_fieldmap else None
+    if out_host is not None:
+        mask, fm = out_host
+        assert mask.dtype == np.uint8 and mask.shape == (n, n, n) and mask.flags.c_contiguous
+        if spec.has_fieldmap:
+            assert fm is not None and fm.dtype == np.float32 and fm.shape == (n, n, n) and fm.flags.c_contiguous
+        else:
+            fm = None
+    else:
+        mask = np.empty((n, n, n), np.uint8)
+        fm = np.empty((n, n, n), np.float32) if spec.has_fieldmap else None
     _ck(lib, lib.swk_phantom_generate(int(device), C.byref(cs), mask.ctypes.data, None if fm is None else fm.ctypes.data, 0, C.byref(st)))
     return mask, fm, fov, st.asdict()

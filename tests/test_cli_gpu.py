@@ -173,19 +173,21 @@ def test_cli_whole_workflow_config_phantom_dwi_sim(cli, tmp_path):
     """The demo notebooks' chain, every step through this CLI: phantom -> config -> dwi -> sim.  Free diffusion (P_XY = 1 everywhere,
     no relaxation) must give the Stejskal-Tanner answer exp(-b D) per b-value (demo/spinwalk_dwi.ipynb)."""
     ph = str(tmp_path / "phantoms" / "spheres.h5")
-    r = subprocess.run([cli, "phantom", "-s", "-r", "-6", "-v", "20", "-f", "60", "-z", "48", "-y", "-1", "-e", "9", "-o", ph, "-q"], capture_output=True, text=True)
+    # FoV 1 mm: with CROSS_FOV = 1 a spin that wraps around the FoV jumps by one FoV in the gradient's frame and is lost to the signal
+    # (~1 % of the spins at 9 um rms displacement; the notebook's own fit of the reference's output has a = 0.9945 for the same reason)
+    r = subprocess.run([cli, "phantom", "-s", "-r", "-60", "-v", "5", "-f", "1000", "-z", "64", "-y", "-1", "-e", "9", "-o", ph, "-q"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     cfg = str(tmp_path / "cfg" / "pgse.ini")
     r = subprocess.run([cli, "config", "-s", "GRE", "-p", ph, "-e", "40000", "-t", "50", "-o", cfg], capture_output=True, text=True)
     assert r.returncode == 0 and "Configuration file is generated in" in r.stdout, r.stderr
-    b = [200, 1000, 3000]
+    b = [200, 600, 1000, 1500]
     r = subprocess.run([cli, "dwi", "-b", *map(str, b), "-v", "1", "0", "0", "-d", "5", "10", "20", "-c", cfg], capture_output=True, text=True)
     assert r.returncode == 0 and "generated successfully" in r.stdout, r.stderr
     # the notebook then edits the tissue parameters by hand: free diffusion, no relaxation, a fixed seed, more spins
     default = str(tmp_path / "cfg" / "default_config.ini")
     txt = open(default).read()
     for old, new in (("P_XY[0] = 1.0 0.0", "P_XY[0] = 1.0 1.0"), ("P_XY[1] = 0.0 1.0", "P_XY[1] = 1.0 1.0"), ("T1[0] = 2200", "T1[0] = -1"), ("T1[1] = 2200", "T1[1] = -1"),
-                     ("T2[0] = 41", "T2[0] = -1"), ("T2[1] = 41", "T2[1] = -1"), ("SEED = 0", "SEED = 7"), ("NUMBER_OF_SPINS = 1e5", "NUMBER_OF_SPINS = 40000"),
+                     ("T2[0] = 41", "T2[0] = -1"), ("T2[1] = 41", "T2[1] = -1"), ("SEED = 0", "SEED = 7"), ("NUMBER_OF_SPINS = 1e5", "NUMBER_OF_SPINS = 2e5"),
                      ("CROSS_FOV = 0", "CROSS_FOV = 1")):
         assert old in txt
         txt = txt.replace(old, new)
@@ -194,8 +196,9 @@ def test_cli_whole_workflow_config_phantom_dwi_sim(cli, tmp_path):
     assert r.returncode == 0, r.stderr
     out = str(tmp_path / "cfg" / "outputs" / "gre_spheres.h5")  # {OUTPUT_DIR}/{SEQ_NAME}_{phantom stem}.h5 (config_reader.cpp:266-271)
     M = h5util.read(out, "M")
-    assert M.shape == (3, 40000, 1, 3)
-    sig = np.hypot(M[..., 0].mean(axis=1), M[..., 1].mean(axis=1)).ravel()
-    want = np.exp(-np.asarray(b, np.float64) * 1e6 * 1.0e-9)  # b in s/mm^2 -> s/m^2, D = 1e-9 m^2/s
-    # Monte-Carlo standard error of |<exp(i phi)>| with 4e4 spins is <= 0.005; the reference's discrete gradient samples add ~1 % in b
-    assert np.all(np.abs(sig - want) < 0.02 + 0.03 * want), (sig, want)
+    assert M.shape == (4, 200000, 1, 3)
+    sig = np.hypot(M[..., 0].astype(np.float64).mean(axis=1), M[..., 1].astype(np.float64).mean(axis=1)).ravel()
+    slope, intercept = np.polyfit(np.asarray(b, np.float64) * 1e6, np.log(sig), 1)  # b in s/mm^2 -> s/m^2; simulated D = 1e-9 m^2/s
+    # same windows as tests/test_engine_gpu.py::test_fast_pgse_free_diffusion_known_answer (Monte-Carlo error of |S| ~ 2e-3 at 2e5 spins)
+    assert abs(-slope / 1e-9 - 1.0) < 0.04, f"fitted D = {-slope:.3e}, a = {np.exp(intercept):.4f}, S = {sig}"
+    assert abs(np.exp(intercept) - 1.0) < 0.015, f"fitted D = {-slope:.3e}, a = {np.exp(intercept):.4f}, S = {sig}"

@@ -118,7 +118,7 @@ def test_engine_resident_phantom_feeds_the_walk(pg, pp):
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     assert np.array_equal(sa[..., 3], sb[..., 3])
-    assert np.allclose(sa, sb, rtol=1e-9, atol=1e-6)  # FP64 atomics: only the association order of the ensemble sums differs
+    assert np.allclose(sa, sb, rtol=1e-5, atol=1e-4)  # FP32 shared-memory + FP64 global atomics: only the association order of the ensemble sums differs
 
 
 def test_generator_error_conventions(pg):
