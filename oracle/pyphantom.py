@@ -56,7 +56,7 @@ def oracle(zwin=None, **kw) -> Phantom:
     calc = a["Y"] >= 0 and a["shape"] != TWOPOOLS
     mask = np.zeros((n, n, zhi - zlo), np.uint8)
     fm = np.zeros((n, n, zhi - zlo), np.float32) if calc else None
-    cap = 1 << 16
+    cap = 1 << 18
     shapes = np.zeros((cap, 4), np.float32)
     ns = C.c_uint32(0)
     bvf = C.c_float(0)
@@ -74,7 +74,7 @@ def oracle_shapes(**kw) -> np.ndarray:
     a = _args(kw)
     lib = C.CDLL(LIB_ORACLE)
     sp = _Spec(a["shape"], a["fov_um"], int(a["resolution"]), a["dchi"], a["Y"], a["radius_um"], a["volume_fraction"], a["orientation_deg"], a["seed"])
-    cap = 1 << 16
+    cap = 1 << 18
     shapes = np.zeros((cap, 4), np.float32)
     ns = C.c_uint32(0)
     rc = lib.swo_phantom_shapes(C.byref(sp), shapes.ctypes.data_as(C.c_void_p), cap, C.byref(ns))
@@ -91,7 +91,7 @@ def reference(omp: bool = False, **kw) -> Phantom:
     calc = a["Y"] >= 0 and a["shape"] != TWOPOOLS
     mask = np.zeros((n, n, n), np.uint8)
     fm = np.zeros((n, n, n), np.float32) if calc else None
-    cap = 1 << 16
+    cap = 1 << 18
     shapes = np.zeros((cap, 4), np.float32)
     ns = C.c_uint32(0)
     bvf = C.c_float(0)

@@ -156,8 +156,13 @@ inline float cylinder_volume(const std::vector<float> &g, float fov, size_t res,
 // The reference's placement loops have no exit when the target cannot be met (e.g. the remaining volume is smaller than any
 // candidate the grid can count): `spinwalk phantom` then spins forever.  This engine gives up after this many consecutive
 // rejected candidates and reports an error instead — the only deliberate deviation in the placement.
-constexpr uint64_t kMaxConsecutiveRejections = 50ull * 1000 * 1000;
 constexpr int SWK_PLACE_STALLED = -1;
+inline uint64_t max_consecutive_rejections()
+{
+    const char *v = getenv("SWK_PHANTOM_MAX_REJECTIONS"); // tests shorten the wait
+    const uint64_t n = v ? strtoull(v, nullptr, 10) : 0;
+    return n ? n : 50ull * 1000 * 1000;
+}
 
 inline uint64_t resolve_seed(int32_t seed) { return seed >= 0 ? uint64_t(seed) : uint64_t(std::random_device{}()); }
 
@@ -174,6 +179,7 @@ inline int place_cylinders(const swk_phantom_spec &sp, const std::vector<float> 
     out.clear();
     CentreGrid<2> grid(-double(rmax), double(fov) + rmax, rmax); // centres lie in [-r, fov + r]
     std::vector<std::pair<uint32_t, float>> near;
+    const uint64_t kMaxConsecutiveRejections = max_consecutive_rejections();
     uint64_t rejected = 0;
     for (int32_t percent = 0; percent < 100;) {
         if (rejected++ > kMaxConsecutiveRejections) return SWK_PLACE_STALLED;
@@ -205,6 +211,7 @@ inline int place_spheres(const swk_phantom_spec &sp, std::vector<Shape> &out)
     out.clear();
     CentreGrid<3> grid(0.0, double(fov), rmax); // centres lie in [0, fov)
     std::vector<std::pair<uint32_t, float>> near;
+    const uint64_t kMaxConsecutiveRejections = max_consecutive_rejections();
     uint64_t rejected = 0;
     for (int32_t percent = 0; percent < 100;) {
         if (rejected++ > kMaxConsecutiveRejections) return SWK_PLACE_STALLED;

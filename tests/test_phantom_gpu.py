@@ -126,3 +126,29 @@ def test_generator_error_conventions(pg):
         pg.generate(pg.PhantomSpec(shape=1, fov_um=10.0, resolution=8, radius_um=6.0, seed=1))
     with pytest.raises(pg.PhantomError, match="no usable CUDA device"):
         pg.generate(pg.PhantomSpec(shape=2, fov_um=10.0, resolution=8), device=99)
+
+
+def test_generator_random_specs_bit_exact(pg, pp, monkeypatch):
+    """Randomised `spinwalk phantom` options (seeded): resolutions that are not multiples of the 8x8x32 sphere tile or of the
+    4096-voxel broadcast chunk, radii below and above the voxel size, every orientation, with and without field map."""
+    import random
+
+    monkeypatch.setenv("SWK_PHANTOM_MAX_REJECTIONS", "200000")
+    rnd = random.Random(20241017)
+    done = 0
+    while done < 16:
+        shape = rnd.choice([0, 1])
+        fov = float(np.float32(rnd.uniform(20.0, 300.0)))
+        res = rnd.choice([7, 9, 16, 17, 23, 31, 33, 40, 47])
+        random_radius = rnd.random() < 0.6
+        rfrac = rnd.uniform(0.03, 0.2)
+        kw = dict(shape=shape, fov_um=fov, resolution=res, radius_um=float(np.float32(fov * rfrac)) * (-1.0 if random_radius else 1.0),
+                  volume_fraction=float(np.float32(rnd.uniform(1.0, 12.0) if random_radius else rnd.uniform(8.0, 20.0))), Y=rnd.choice([-1.0, 0.0, 0.6, 0.78, 1.0]),
+                  orientation_deg=float(np.float32(rnd.uniform(-10.0, 190.0))), dchi=rnd.choice([0.11e-6, 0.273e-6 * 0.4]), seed=rnd.randint(0, 2 ** 31 - 1))
+        try:
+            mask, fm, _, st = pg.generate(spec_of(pg, kw))
+        except pg.PhantomError as e:
+            assert "does not converge" in str(e)
+            continue
+        assert_same(mask, fm, st, pp.oracle(**kw))
+        done += 1

@@ -121,3 +121,37 @@ def test_voxel_fill_has_no_cpu_path(engine_lib):
         pytest.skip("a GPU is visible here")
     with pytest.raises(pg.PhantomError, match="no usable CUDA device"):
         pg.generate(pg.PhantomSpec(shape=2, fov_um=50.0, resolution=16))
+
+
+def test_product_placement_random_specs(pp, engine_lib, monkeypatch):
+    """Randomised `spinwalk phantom` options (hypothesis): the product's grid-accelerated placement must give the oracle's shape list,
+    bit for bit — fixed and random radii, cylinders and spheres, low and high packing, shapes smaller and larger than a voxel."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from spinwalk_b200 import phantom_gen as pg
+
+    monkeypatch.setenv("SWK_PHANTOM_MAX_REJECTIONS", "200000")  # specs the reference would never finish are given up quickly
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(shape=st.sampled_from([0, 1]), fov=st.floats(20.0, 400.0), res=st.integers(8, 64), rfrac=st.floats(0.03, 0.2), random_radius=st.booleans(),
+           vf=st.floats(0.5, 12.0), seed=st.integers(0, 2 ** 31 - 1))
+    def check(shape, fov, res, rfrac, random_radius, vf, seed):
+        fov = float(np.float32(fov))
+        radius = float(np.float32(fov * rfrac)) * (-1.0 if random_radius else 1.0)
+        vf = float(np.float32(vf if random_radius else max(vf, 4.0)))  # fixed radii: leave room for whole shapes (the reference never ends otherwise)
+        if not random_radius and shape == 0:
+            # a fixed-radius cylinder adds pi r^2 / fov^2 of the volume at once: keep the target reachable within the 1.02 tolerance
+            one = np.pi * rfrac ** 2 * 100.0
+            vf = float(np.float32(one * max(1, round(vf / one))))
+        kw = dict(shape=shape, fov_um=fov, resolution=res, radius_um=radius, volume_fraction=vf, Y=-1.0, seed=seed)
+        spec = pg.PhantomSpec(shape=shape, fov_um=fov, resolution=res, oxy_level=-1.0, radius_um=radius, volume_fraction=vf, seed=seed)
+        try:
+            got = pg.shapes(spec)
+        except pg.PhantomError as e:
+            assert "does not converge" in str(e)  # the reference would loop forever: nothing to compare
+            return
+        want = pp.oracle_shapes(**kw)
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+    check()
