@@ -68,7 +68,7 @@ def workload(name: str, n_spins: int | None, n_scales: int | None):
         cfg = dict(base, TR_us=60050, TE_us=[60000], T1_ms=[9999999.0, 9999999.0], T2_ms=[9999999.0, 9999999.0],
                    pXY=[1.0, 0.05, 0.05, 1.0] if restricted else [1.0, 1.0, 1.0, 1.0], cross_fov=1, **seq)
         ph = dict(kind="spheres", n=400, fov_um=400.0, cell_um=40.0, vf=40.0, seed=0)
-        S, desc = 10_000_000, ("C3 PGSE (dwi -b 100..5000,0 -v 1 0 0 -d 15 10 20), 400^3 sphere phantom (r <= 20 um, 38 %), no fieldmap, "
+        S, desc = 10_000_000, ("C3 PGSE (dwi -b 100..5000,0 -v 1 0 0 -d 15 10 20), 400^3 sphere phantom (phantom -s -r -20 -v 40 -y -1 -e 0), no fieldmap, "
                                + ("P_XY = 0.05 (restricted)" if restricted else "P_XY = 1 (free diffusion)") + ", 1e7 spins, 51 gradient scales")
     else:
         raise SystemExit(f"unknown workload {name}")
@@ -87,6 +87,16 @@ def make_phantom_2d(ph):
     if ph["kind"] == "spheres":
         return sphere_lattice_phantom(ph["n"], ph["fov_um"], ph["cell_um"], ph["vf"], ph["seed"])
     return cylinder_phantom(ph["n"], ph["fov_um"], radius_um=ph["radius_um"], bvf_pct=ph["bvf"], Y=ph["Y"], seed=ph["seed"], planar=True)
+
+
+def phantom_spec(ph):
+    """The `spinwalk phantom` invocation of a workload's phantom as a spinwalk_b200.phantom_gen.PhantomSpec."""
+    from spinwalk_b200 import phantom_gen as pg
+
+    if ph["kind"] == "spheres":  # demo/spinwalk_dwi.ipynb: -s -r -20 -v 40 -y -1 -e 0
+        return pg.PhantomSpec(shape=pg.SHAPE_SPHERE, fov_um=ph["fov_um"], resolution=ph["n"], oxy_level=-1.0, radius_um=-20.0, volume_fraction=ph["vf"], seed=ph["seed"])
+    return pg.PhantomSpec(shape=pg.SHAPE_CYLINDER, fov_um=ph["fov_um"], resolution=ph["n"], oxy_level=ph["Y"], radius_um=ph["radius_um"], volume_fraction=ph["bvf"],
+                          orientation_deg=90.0, seed=ph["seed"])
 
 
 def full_phantom(ph, mask2, fm2):
@@ -408,24 +418,16 @@ def main():
     mode = sw.MODE_FAST if args.mode == "fast" else sw.MODE_COMPAT
     cfg_kw_global = dict(cfg_kw, n_spins=S_per_gpu * world)  # weak scaling: global population grows with N
     cfg = sw.SimConfig(**cfg_kw_global)
-    mask2, fm2, fov = make_phantom_2d(ph)
-    n = ph["n"]
-    if mask2.ndim == 3:
-        mask_d = torch.from_numpy(mask2).to(dev)
-        fm_d = None if fm2 is None else torch.from_numpy(fm2).to(dev)
-    else:
-        mask_d = torch.from_numpy(mask2).to(dev)[:, :, None].expand(n, n, n).contiguous()
-        fm_d = torch.from_numpy(fm2).to(dev)[:, :, None].expand(n, n, n).contiguous()
+    # the phantom: the reference's own recipe (`spinwalk phantom ...`), generated on every rank's device by the product generator
+    # (include/spinwalk_phantom.h: bit-identical to the reference's generator, tests/test_phantom_gpu.py) — it never visits the host
+    eng = sw.Engine(local_rank)
+    gen = eng.generate_phantom(phantom_spec(ph))
+    fov = eng.fov
 
     spin_first, n_local = sharding.shard_range(S_per_gpu * world, rank, world)  # weak scaling: S_per_gpu spins on every rank
     assert n_local == S_per_gpu
     xyz0_pin = torch.empty((S_per_gpu, 3), dtype=torch.float32, pin_memory=True)
     xyz0_pin.numpy()[:] = make_positions(S_per_gpu, fov, cfg.seed, spin_first)
-
-    eng = sw.Engine(local_rank)
-    eng.set_phantom(mask_d, fm_d, fov)
-    del mask_d, fm_d
-    torch.cuda.empty_cache()
     per_spin_out = args.workload != "c5"  # C5: 1e9 spins x 50 scales of per-spin output would be 650 GB: the reduce is the product
     out_flags = sw.OUT_ALL if per_spin_out else 0
     eng.set_sequence(cfg)
@@ -542,11 +544,15 @@ def main():
                        "scans": eng.n_dummy_scan + 1, "spin_steps_per_pass": steps_per_pass_rank * world,
                        "rng": "philox4x32-10, one block per two steps + Box-Muller (SWK_MODE_FAST)" if mode == sw.MODE_FAST else "minstd_rand + erfcinvf (SWK_MODE_COMPAT, reference arithmetic)",
                        "l2": f"inputs larger than L2 (phantom {5 * ph['n'] ** 3 / 1e9:.2f} GB vs 126 MB)" if ph["n"] >= 600 else "phantom fits in L2; outputs (12.5 GB > L2) rewritten every pass",
+                       "phantom": f"generated on the device by swk_generate_phantom: {gen['n_shapes']} shapes, volume fraction {gen['volume_fraction']:.3f} %, "
+                                  f"voxel fill {gen['kernel_ms']:.2f} ms (bit-identical to the reference's `spinwalk phantom` for this recipe)",
                        "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums"},
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": args.steps * st["n_launches"],
             "e2e": e2e, "roofline": roofline, "lost_spins": st_counts["lost"]}
 
+    mask2 = fm2 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload != "c5":  # (C5's 5 GB host phantom: use C2's baseline)
+        mask2, fm2 = eng.get_phantom()  # the baselines below walk the very same voxels
         try:
             cb, _, _ = cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0)
             line["cpu_baseline"] = cb
