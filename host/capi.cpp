@@ -146,3 +146,25 @@ int swkh_ini_edit(const char *path, int n, const int *ops, const char *const *se
 }
 
 } // extern "C"
+
+#include "ply_reader.h"
+
+extern "C" {
+
+// PLY reader for the tests: call with vertices == NULL to get the sizes, again with buffers to get the data.  0 ok, 1 failed (message in buf).
+int swkh_ply_read(const char *path, double *vertices, uint64_t *n_vertices, uint64_t *faces, uint64_t *n_faces, char *buf, size_t n)
+{
+    swk_host::PlyMesh m;
+    std::string err;
+    if (!swk_host::read_ply(path, m, err)) {
+        if (buf && n) copy_out(err, buf, n);
+        return 1;
+    }
+    if (vertices && *n_vertices >= m.n_vertices()) memcpy(vertices, m.vertices.data(), m.vertices.size() * sizeof(double));
+    if (faces && *n_faces >= m.n_faces()) memcpy(faces, m.faces.data(), m.faces.size() * sizeof(uint64_t));
+    *n_vertices = m.n_vertices();
+    *n_faces = m.n_faces();
+    return 0;
+}
+
+} // extern "C"

@@ -5,7 +5,7 @@
 //   spinwalk config  -s SEQ -p PHANTOM... -e TE -t DT -o FILE     GRE / SE / bSSFP configuration (:73-78)
 //   spinwalk dwi     -b B... -v X Y Z -d START δ Δ -c CONFIG      PGSE gradient table into a config (:80-84)
 // Option names, defaults and mandatory flags follow the reference.  This build has no CPU path: `sim -p` is accepted and refused
-// with a clear message; `phantom -p` (ply meshes) is not provided.  Extensions: -d takes a comma-separated list (spins sharded over
+// with a clear message.  Extensions: -d takes a comma-separated list (spins sharded over
 // several GPUs), --compat selects the reference-arithmetic kernel, --sums adds the ensemble sums to the output file, -q is quiet.
 #include <cstdio>
 #include <cstdlib>
@@ -28,7 +28,7 @@ void usage()
             "  sim      -c,--configs FILE...   config. files as many as you want\n"
             "           -p,--use_cpu           not available: this engine has no CPU path\n"
             "           -d,--device N[,M...]   select GPU device(s); [--compat] [--sums] [-q]\n"
-            "  phantom  -c,--cylinder | -s,--sphere | -t,--two_pools   shape (-p,--ply is not provided)\n"
+            "  phantom  -c,--cylinder | -s,--sphere | -t,--two_pools | -p,--ply -i,--ply_file MESH.ply\n"
             "           -r,--radius [50]  -n,--orientation [90]  -v,--volume_fraction [4]  -f,--fov (required)  -z,--resolution (required)\n"
             "           -d,--dchi [0.11e-6]  -y,--oxy_level [0.75]  -e,--seed [-1]  -o,--output (required)  [--device N]\n"
             "  config   -s,--seq_name GRE|SE|bSSFP  -p,--phantoms FILE...  -e,--TE us  -t,--timestep us  -o,--output FILE\n"
@@ -116,7 +116,10 @@ int run_phantom(Args &a)
         } else if (o == "-d" || o == "--dchi") { if (!a.one(v) || !to_float(v, p.dchi)) return fail_usage("--dchi: a number is required"); }
         else if (o == "-y" || o == "--oxy_level") { if (!a.one(v) || !to_float(v, p.oxy_level)) return fail_usage("--oxy_level: a number is required"); }
         else if (o == "-e" || o == "--seed") { if (!a.one(v)) return fail_usage("--seed: a number is required"); p.seed = atoi(v.c_str()); }
-        else if (o == "-i" || o == "--ply_file") { if (!a.one(p.ply_file)) return fail_usage("--ply_file: a path is required"); }
+        else if (o == "-i" || o == "--ply_file") {
+            if (!a.one(p.ply_file)) return fail_usage("--ply_file: a path is required");
+            if (!std::filesystem::exists(p.ply_file)) return fail_usage("--ply_file: File does not exist: " + p.ply_file);
+        }
         else if (o == "-o" || o == "--output") { if (!a.one(p.output)) return fail_usage("--output: a path is required"); }
         else if (o == "--device") { if (!a.one(v)) return fail_usage("--device: a number is required"); p.device = atoi(v.c_str()); }
         else return fail_usage("The following argument was not expected: " + o);
@@ -124,6 +127,7 @@ int run_phantom(Args &a)
     if (!have_fov) return fail_usage("--fov is required");
     if (!have_res) return fail_usage("--resolution is required");
     if (p.output.empty()) return fail_usage("--output is required");
+    if (p.ply && p.ply_file.empty()) return fail_usage("--ply needs --ply_file");
     const int n_sel = int(p.cylinder) + int(p.sphere) + int(p.twopools) + int(p.ply);
     if (n_sel == 0 || n_sel == 4) { // src/spinwalk.cpp:91-96
         if (n_sel == 4) printf("Error! select either --cylinder or --sphere, not both!\n");

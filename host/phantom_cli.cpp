@@ -1,4 +1,4 @@
-// host/phantom_cli.cpp — `spinwalk phantom`: the reference's phantom::handler::execute (src/phantom/handler.cpp:10-35) on the GPU
+// host/phantom_cli.cpp — `spinwalk phantom` (-c / -s / -t / -p): the reference's phantom::handler::execute (src/phantom/handler.cpp:10-35) on the GPU
 // generator (include/spinwalk_phantom.h), writing the phantom file of phantom_base::save (src/phantom/phantom_base.cpp:69-103):
 // datasets /fieldmap (float32 [n,n,n], only when oxy_level >= 0), /mask (uint8 [n,n,n]), /fov (float32 [3], metres), /bvf (float32 [1]).
 #include <cstdio>
@@ -8,6 +8,7 @@
 #include "../include/spinwalk_phantom.h"
 #include "generators.h"
 #include "h5lite.h"
+#include "ply_reader.h"
 
 namespace fs = std::filesystem;
 
@@ -59,6 +60,34 @@ bool one_phantom(const PhantomArgs &a, int shape, const char *what, std::string 
     if (!w.close()) { error = w.error(); return false; }
     return true;
 }
+// ≙ phantom::ply::run(true) (src/phantom/phantom_ply.cpp:141-255): mask only; the reference leaves `bvf` at 0 for mesh phantoms (:187)
+bool mesh_phantom(const PhantomArgs &a, std::string &error)
+{
+    if (!a.quiet) printf("Generating phantom from triangular mesh...\n");
+    PlyMesh mesh;
+    if (!read_ply(a.ply_file, mesh, error)) return false;
+    const size_t n = a.resolution, V = n * n * n;
+    std::vector<uint8_t> mask(V);
+    swk_phantom_stats st{};
+    if (swk_phantom_mesh(a.device, a.fov, a.resolution, mesh.vertices.data(), mesh.n_vertices(), mesh.faces.data(), mesh.n_faces(), mask.data(), 0, &st) != SWK_OK) {
+        error = swk_phantom_last_error();
+        return false;
+    }
+    if (!a.quiet)
+        printf("%zu vertices, %zu triangles, %g %% of the voxels inside; mesh preparation %.1f ms, voxel fill on the GPU %.2f ms\n", mesh.n_vertices(), mesh.n_faces(),
+               st.volume_fraction, st.place_ms, st.kernel_ms);
+    const fs::path parent = fs::absolute(a.output).parent_path();
+    std::error_code ec;
+    if (!fs::is_directory(parent) && !fs::create_directories(parent, ec)) { error = "cannot create directory " + parent.string(); return false; }
+    const float fov_m[3] = {a.fov * 1e-6f, a.fov * 1e-6f, a.fov * 1e-6f};
+    const float bvf = 0.f;
+    h5::Writer w(a.output);
+    w.add("mask", {n, n, n}, h5::DType::U8, mask.data());
+    w.add("fov", {3}, h5::DType::F32, fov_m);
+    w.add("bvf", {1}, h5::DType::F32, &bvf);
+    if (!w.close()) { error = w.error(); return false; }
+    return true;
+}
 } // namespace
 
 bool generate_phantom(const PhantomArgs &a, std::string &error)
@@ -67,10 +96,7 @@ bool generate_phantom(const PhantomArgs &a, std::string &error)
     if (a.cylinder) ok = ok && one_phantom(a, SWK_SHAPE_CYLINDER, "cylinder phantom", error);
     if (a.sphere) ok = ok && one_phantom(a, SWK_SHAPE_SPHERE, "sphere phantom", error);
     if (a.twopools) ok = ok && one_phantom(a, SWK_SHAPE_TWOPOOLS, "phantom with two pools", error);
-    if (a.ply) {
-        error = "the triangular-mesh (ply) phantom of the reference is not provided by this build";
-        ok = false;
-    }
+    if (a.ply) ok = ok && mesh_phantom(a, error);
     if (ok && !a.quiet) printf("Done.\n");
     return ok;
 }

@@ -1,6 +1,6 @@
 /* include/spinwalk_phantom.h — C-ABI of the B200 phantom generator (part of libspinwalk_b200.so).
  *
- * the producer on the input side of the `sim` hot path.  Replaces, for cylinders / spheres / two pools,
+ * the producer on the input side of the `sim` hot path.  Replaces
  *      src/phantom/handler.cpp:10-35                  phantom::handler::execute (what `spinwalk phantom` calls)
  *      src/phantom/phantom_base.cpp:107-143           voxel-centre grid (12 B per voxel on the host in the reference)
  *      src/phantom/phantom_cylinder.cpp:85-130        random placement of parallel cylinders (sequential host RNG)
@@ -8,11 +8,11 @@
  *      src/phantom/phantom_sphere.cpp:79-119          random placement of spheres
  *      src/phantom/phantom_sphere.cpp:121-198         mask + dipole field of spheres             -> CUDA kernel
  *      src/phantom/phantom_twopools.cpp:40-63         half/half mask
+ *      src/phantom/phantom_ply.cpp:141-227            closed triangle mesh -> mask (ray parity)  -> CUDA kernel (swk_phantom_mesh)
  * The shape placement is inherently sequential (every accepted shape changes the acceptance test of the next) and stays on
  * the host with the reference's engines (std::mt19937 / std::minstd_rand, uniform_real_distribution<float>); the O(V x shapes)
  * voxel fill runs on the device, with the reference's float/double expression order, so that the mask and the field map
  * are bit-identical to a serial x86-64 build of the reference (tests/test_phantom_gpu.py).
- * The PLY (triangle mesh) phantom of the reference (phantom_ply.cpp) is not provided.
  *
  * Conventions as in spinwalk_engine.h: plain C, int status (SWK_OK == 0), caller owns host buffers, no CPU fallback for
  * the voxel fill (swk_phantom_generate fails without a CUDA device; swk_phantom_shapes is host-only by nature).
@@ -70,6 +70,15 @@ int swk_generate_phantom(swk_engine *e, const swk_phantom_spec *spec, swk_phanto
 
 /* Copies the engine's current phantom to host buffers (either may be NULL), e.g. to save a generated phantom. */
 int swk_get_phantom(swk_engine *e, uint8_t *mask, float *fieldmap_T);
+
+/* Triangle-mesh phantom (≙ phantom::ply::run(false), src/phantom/phantom_ply.cpp:141-227, `spinwalk phantom -p -i mesh.ply`).
+ * vertices: double [n_vertices][3] in the PLY file's unit (mm; converted to µm and centred in the FoV like the reference, :160-175);
+ * faces: [n_faces][3] vertex indices (triangles only).  mask: uint8 [res][res][res], x slowest, 1 where the +x ray from the voxel
+ * centre hits an odd number of triangles — bit-identical to the reference (same BVH leaf boxes, same mixed double/float hit test).
+ * No field map (the reference forces Y = -1).  stats->n_shapes = n_faces; stats->volume_fraction is the actual percentage (the
+ * reference leaves the `bvf` dataset of a mesh phantom at 0; the CLI writes 0 as well). */
+int swk_phantom_mesh(int device, float fov_um, uint64_t resolution, const double *vertices, uint64_t n_vertices, const uint64_t *faces,
+                     uint64_t n_faces, uint8_t *mask, int on_device, swk_phantom_stats *stats);
 
 const char *swk_phantom_last_error(void); /* message of the last failed swk_phantom_* call on this thread */
 

@@ -401,3 +401,123 @@ int swo_phantom_generate(const swo_phantom_spec *s, uint8_t *mask, float *fieldm
     if (rc == 0 && bvf) *bvf = volume_fraction(mask, res * res * res);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * Triangle-mesh phantom (`spinwalk phantom -p -i mesh.ply`): src/phantom/phantom_ply.cpp:141-227 + helpers :27-134.
+ * A voxel centre is inside the mesh when the ray (1,0,0) from it hits an odd number of triangles (Möller-Trumbore in mixed
+ * double / float arithmetic, :90-111).  The reference walks a median-split BVH whose boxes only prune on (y, z) (:37-88,
+ * phantom_ply.h:37-42), so a triangle is tested for a ray exactly when the ray's (y, z) lies inside the box of the LEAF that
+ * holds the triangle (a leaf box lies inside all its ancestors' boxes).  The BVH is rebuilt here with the same median splits
+ * (qsort instead of std::sort: triangles with equal centroid keys may land in different leaves, which can only matter for a ray
+ * through the exact edge of a leaf box); the hit count then runs over all triangles with the leaf-box test in place.
+ * vertices: double [nv][3] as the PLY file holds them (mm); faces: [nf][3] vertex indices.
+ * ------------------------------------------------------------------------------------------------------------------------ */
+typedef struct { double x, y, z; } vec3;
+typedef struct { vec3 v0, v1, v2; double ymin, ymax, zmin, zmax; } mtri;
+
+static int g_axis;
+static double coord(const vec3 *v, int ax) { return ax == 0 ? v->x : ax == 1 ? v->y : v->z; }
+static int cmp_centroid(const void *pa, const void *pb)
+{ /* :62-66: (c0 + c1 + c2) / 3.0f in double */
+    const mtri *a = pa, *b = pb;
+    double ca = (coord(&a->v0, g_axis) + coord(&a->v1, g_axis) + coord(&a->v2, g_axis)) / 3.0f;
+    double cb = (coord(&b->v0, g_axis) + coord(&b->v1, g_axis) + coord(&b->v2, g_axis)) / 3.0f;
+    return ca < cb ? -1 : (cb < ca ? 1 : 0);
+}
+static void tri_box(const mtri *t, size_t start, size_t end, vec3 *mn, vec3 *mx)
+{ /* computeAABB :43-52 */
+    mn->x = mn->y = mn->z = 1.7976931348623157e308;
+    mx->x = mx->y = mx->z = -1.7976931348623157e308;
+    for (size_t i = start; i < end; i++) {
+        const vec3 *v[3] = {&t[i].v0, &t[i].v1, &t[i].v2};
+        for (int k = 0; k < 3; k++) {
+            if (v[k]->x < mn->x) mn->x = v[k]->x;
+            if (v[k]->y < mn->y) mn->y = v[k]->y;
+            if (v[k]->z < mn->z) mn->z = v[k]->z;
+            if (v[k]->x > mx->x) mx->x = v[k]->x;
+            if (v[k]->y > mx->y) mx->y = v[k]->y;
+            if (v[k]->z > mx->z) mx->z = v[k]->z;
+        }
+    }
+}
+static void build_leaves(mtri *t, size_t start, size_t end)
+{ /* buildBVH :73-86 + partitionTriangles :54-71 */
+    vec3 mn, mx;
+    tri_box(t, start, end, &mn, &mx);
+    if (end - start <= 4) {
+        for (size_t i = start; i < end; i++) { t[i].ymin = mn.y; t[i].ymax = mx.y; t[i].zmin = mn.z; t[i].zmax = mx.z; }
+        return;
+    }
+    double ex = mx.x - mn.x, ey = mx.y - mn.y, ez = mx.z - mn.z;
+    int axis = 0;
+    if (ey > ex) axis = 1;
+    if (ez > (ex > ey ? ex : ey)) axis = 2;
+    g_axis = axis;
+    qsort(t + start, end - start, sizeof(mtri), cmp_centroid);
+    size_t mid = start + (end - start) / 2;
+    build_leaves(t, start, mid);
+    build_leaves(t, mid, end);
+}
+
+/* rayIntersectsTriangle :90-111 with dir = (1,0,0); every product / sum in the reference's type and order */
+static int ray_hits(const vec3 *o, const mtri *tr)
+{
+    const float EPSILON = 1e-6f;
+    const vec3 dir = {1., 0., 0.};
+    vec3 e1 = {tr->v1.x - tr->v0.x, tr->v1.y - tr->v0.y, tr->v1.z - tr->v0.z};
+    vec3 e2 = {tr->v2.x - tr->v0.x, tr->v2.y - tr->v0.y, tr->v2.z - tr->v0.z};
+    vec3 h = {dir.y * e2.z - dir.z * e2.y, dir.z * e2.x - dir.x * e2.z, dir.x * e2.y - dir.y * e2.x};
+    float a = (float)(e1.x * h.x + e1.y * h.y + e1.z * h.z);
+    if (fabsf(a) < EPSILON) return 0;
+    float f = 1.0f / a;
+    vec3 s = {o->x - tr->v0.x, o->y - tr->v0.y, o->z - tr->v0.z};
+    float u = f * (float)(s.x * h.x + s.y * h.y + s.z * h.z);
+    if (u < 0.0f || u > 1.0f) return 0;
+    vec3 q = {s.y * e1.z - s.z * e1.y, s.z * e1.x - s.x * e1.z, s.x * e1.y - s.y * e1.x};
+    float v = f * (float)(dir.x * q.x + dir.y * q.y + dir.z * q.z);
+    if (v < 0.0f || u + v > 1.0f) return 0;
+    float t = f * (float)(e2.x * q.x + e2.y * q.y + e2.z * q.z);
+    return t >= 0.0f;
+}
+
+int swo_phantom_mesh(float fov_um, uint64_t resolution, const double *vertices, uint64_t n_vertices, const uint64_t *faces, uint64_t n_faces, uint8_t *mask)
+{
+    const size_t res = resolution;
+    if (fov_um == 0 || res == 0) return 1;
+    memset(mask, 0, res * res * res);
+    mtri *t = malloc((n_faces ? n_faces : 1) * sizeof(mtri));
+    for (uint64_t i = 0; i < n_faces; i++) { /* :160-167: mm -> um */
+        const uint64_t *f = faces + 3 * i;
+        if (f[0] >= n_vertices || f[1] >= n_vertices || f[2] >= n_vertices) { free(t); return 2; }
+        t[i].v0 = (vec3){vertices[3 * f[0]] * 1e3, vertices[3 * f[0] + 1] * 1e3, vertices[3 * f[0] + 2] * 1e3};
+        t[i].v1 = (vec3){vertices[3 * f[1]] * 1e3, vertices[3 * f[1] + 1] * 1e3, vertices[3 * f[1] + 2] * 1e3};
+        t[i].v2 = (vec3){vertices[3 * f[2]] * 1e3, vertices[3 * f[2] + 1] * 1e3, vertices[3 * f[2] + 2] * 1e3};
+    }
+    vec3 mn, mx;
+    tri_box(t, 0, n_faces, &mn, &mx);
+    vec3 shift = {(mx.x + mn.x) / 2., (mx.y + mn.y) / 2., (mx.z + mn.z) / 2.}; /* :172: centre the mesh in the FoV */
+    const double half = fov_um / 2.;
+    for (uint64_t i = 0; i < n_faces; i++) {
+        vec3 *v[3] = {&t[i].v0, &t[i].v1, &t[i].v2};
+        for (int k = 0; k < 3; k++) { v[k]->x = v[k]->x + half - shift.x; v[k]->y = v[k]->y + half - shift.y; v[k]->z = v[k]->z + half - shift.z; }
+    }
+    build_leaves(t, 0, n_faces);
+    tri_box(t, 0, n_faces, &mn, &mx); /* root->bounds */
+    float *g = malloc(res * sizeof(float));
+    grid_base(fov_um, res, g);
+    for (size_t px = 0; px < res; px++)
+        for (size_t py = 0; py < res; py++)
+            for (size_t pz = 0; pz < res; pz++) {
+                vec3 o = {g[px], g[py], g[pz]};
+                if (o.x < mn.x || o.x > mx.x || o.y < mn.y || o.y > mx.y || o.z < mn.z || o.z > mx.z) continue; /* :206-207 */
+                unsigned hits = 0;
+                for (uint64_t i = 0; i < n_faces; i++) {
+                    if (o.y < t[i].ymin || o.y > t[i].ymax || o.z < t[i].zmin || o.z > t[i].zmax) continue; /* leaf box (intersectsRay) */
+                    hits += (unsigned)ray_hits(&o, &t[i]);
+                }
+                mask[(px * res + py) * res + pz] = (uint8_t)(hits % 2);
+            }
+    free(g);
+    free(t);
+    return 0;
+}

@@ -31,6 +31,10 @@ int swo_phantom_generate(const swo_phantom_spec *s, uint8_t *mask, float *fieldm
 int swo_phantom_generate_window(const swo_phantom_spec *s, int32_t zlo, int32_t zhi, uint8_t *mask, float *fieldmap, float *shapes, uint32_t cap,
                                 uint32_t *n_shapes);
 
+/* `spinwalk phantom -p`: mask of a closed triangle mesh centred in the FoV.  vertices double [nv][3] in the PLY file's unit (mm),
+ * faces uint64 [nf][3].  Returns 0, 1 (no FoV / resolution) or 2 (face index out of range). */
+int swo_phantom_mesh(float fov_um, uint64_t resolution, const double *vertices, uint64_t n_vertices, const uint64_t *faces, uint64_t n_faces, uint8_t *mask);
+
 #ifdef __cplusplus
 }
 #endif

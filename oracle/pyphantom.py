@@ -116,3 +116,29 @@ def reference_config(seq_name: str, TE_us: int, timestep_us: int, phantoms, outp
     lib = C.CDLL(LIB_REF)
     arr = (C.c_char_p * len(phantoms))(*[p.encode() for p in phantoms])
     return lib.swref_config(seq_name.encode(), int(TE_us), int(timestep_us), arr, len(phantoms), output.encode()) == 0
+
+
+def oracle_mesh(fov_um: float, resolution: int, vertices, faces) -> np.ndarray:
+    """C restatement of `spinwalk phantom -p`: vertices float64 [nv,3] in the PLY file's unit (mm), faces [nf,3]."""
+    lib = C.CDLL(LIB_ORACLE)
+    v = np.ascontiguousarray(vertices, np.float64)
+    f = np.ascontiguousarray(faces, np.uint64)
+    n = int(resolution)
+    mask = np.zeros((n, n, n), np.uint8)
+    rc = lib.swo_phantom_mesh(C.c_float(fov_um), C.c_uint64(n), v.ctypes.data_as(C.c_void_p), C.c_uint64(len(v)), f.ctypes.data_as(C.c_void_p), C.c_uint64(len(f)),
+                              mask.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"mesh oracle refused the input (rc={rc})")
+    return mask
+
+
+def reference_mesh(fov_um: float, resolution: int, ply_path: str):
+    """phantom::ply(fov, resolution, ..., ply_path).run(false) of the reference: (mask, bvf)."""
+    lib = C.CDLL(LIB_REF)
+    n = int(resolution)
+    mask = np.zeros((n, n, n), np.uint8)
+    bvf = C.c_float(-1)
+    rc = lib.swref_phantom_ply(C.c_float(fov_um), C.c_uint64(n), ply_path.encode(), mask.ctypes.data_as(C.c_void_p), C.byref(bvf))
+    if rc != 0:
+        raise RuntimeError(f"reference ply phantom failed (rc={rc})")
+    return mask, bvf.value

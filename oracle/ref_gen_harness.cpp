@@ -17,6 +17,7 @@
 #define private public
 #define protected public
 #include "phantom/phantom_cylinder.h"
+#include "phantom/phantom_ply.h"
 #include "phantom/phantom_sphere.h"
 #include "phantom/phantom_twopools.h"
 #undef private
@@ -86,6 +87,19 @@ int swref_phantom(int shape, float fov_um, uint64_t resolution, float dchi, floa
         return export_phantom(t, resolution, false, mask, nullptr, bvf);
     }
     return 4;
+}
+
+// `spinwalk phantom -p -i ply_file -f fov -z resolution`: mask [res][res][res] of phantom::ply::run(false).
+int swref_phantom_ply(float fov_um, uint64_t resolution, const char *ply_file, uint8_t *mask, float *bvf)
+{
+    quiet_cout q;
+    try {
+        phantom::ply p(fov_um, resolution, 0.11e-6f, -1.f, ply_file, "unused.h5");
+        if (!p.run(false)) return 1;
+        return export_phantom(p, resolution, false, mask, nullptr, bvf);
+    } catch (const std::exception &) { // happly throws on malformed files
+        return 5;
+    }
 }
 
 // `spinwalk dwi -b b... -v x y z -d start delta DELTA -c config` (src/spinwalk.cpp:110-114): edits `config` in place.

@@ -96,6 +96,7 @@ SYMBOLS = {
     "swk_phantom_generate": (C.c_int, [C.c_int, C.POINTER(PhantomSpec), _P, _P, C.c_int, C.POINTER(PhantomStats)]),
     "swk_generate_phantom": (C.c_int, [_P, C.POINTER(PhantomSpec), C.POINTER(PhantomStats)]),
     "swk_get_phantom": (C.c_int, [_P, _P, _P]),
+    "swk_phantom_mesh": (C.c_int, [C.c_int, C.c_float, C.c_uint64, _P, C.c_uint64, _P, C.c_uint64, _P, C.c_int, C.POINTER(PhantomStats)]),
     "swk_phantom_last_error": (C.c_char_p, []),
 }
 

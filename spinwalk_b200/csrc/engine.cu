@@ -930,6 +930,7 @@ uint64_t swk_device_bytes(const swk_engine *e)
 // Phantom generator (include/spinwalk_phantom.h)
 // ------------------------------------------------------------------------------------------------------------------------
 #include "phantom.cuh"
+#include "phantom_mesh.cuh"
 
 namespace {
 thread_local std::string g_phantom_error;
@@ -1020,6 +1021,39 @@ int swk_phantom_generate(int device, const swk_phantom_spec *spec, uint8_t *mask
     }
     if (rc != SWK_OK) return phantom_fail(rc, fr.error);
     fill_stats(stats, *spec, placed, place_ms, fr);
+    return SWK_OK;
+}
+
+int swk_phantom_mesh(int device, float fov_um, uint64_t resolution, const double *vertices, uint64_t n_vertices, const uint64_t *faces, uint64_t n_faces,
+                     uint8_t *mask, int on_device, swk_phantom_stats *stats)
+{
+    if (!mask || (n_vertices && !vertices) || (n_faces && !faces)) return phantom_fail(SWK_ERR_INVALID, "swk_phantom_mesh: vertices, faces and mask are mandatory");
+    if (!(fov_um > 0.f) || resolution == 0) return phantom_fail(SWK_ERR_INVALID, "FOV or resolution is not set"); // phantom_base.cpp:110-114
+    if (resolution > 2048) return phantom_fail(SWK_ERR_INVALID, "resolution above 2048 is not supported");
+    if (n_faces > 0xffffffffull) return phantom_fail(SWK_ERR_INVALID, "more than 2^32 triangles");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev)
+        return phantom_fail(SWK_ERR_CUDA, "swk_phantom_mesh: no usable CUDA device (this library has no CPU path for the voxel fill)");
+    if (cudaSetDevice(device) != cudaSuccess) return phantom_fail(SWK_ERR_CUDA, "cudaSetDevice failed");
+    const size_t V = size_t(resolution) * resolution * resolution;
+    uint8_t *d_mask = mask;
+    if (!on_device && cudaMalloc(&d_mask, V) != cudaSuccess) return phantom_fail(SWK_ERR_MEMORY, "swk_phantom_mesh: cudaMalloc failed");
+    swk::phantom::MeshResult mr;
+    int rc = swk::phantom::fill_mesh_device(fov_um, uint32_t(resolution), vertices, n_vertices, faces, n_faces, d_mask, nullptr, mr);
+    if (rc == SWK_OK && !on_device && cudaMemcpy(mask, d_mask, V, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        rc = SWK_ERR_CUDA;
+        mr.error = "device-to-host copy of the mask failed";
+    }
+    if (!on_device) cudaFree(d_mask);
+    if (rc != SWK_OK) return phantom_fail(rc, mr.error);
+    if (stats) {
+        stats->n_shapes = uint32_t(n_faces);
+        stats->volume_fraction = float(double(mr.ones) * 100.0 / double(V));
+        stats->place_ms = mr.prep_ms; // host: mesh transform, leaf boxes, row binning
+        stats->kernel_ms = mr.kernel_ms;
+        stats->n_launches = 1;
+        stats->exact_columns = 0;
+    }
     return SWK_OK;
 }
 

@@ -98,3 +98,17 @@ def generate(spec: PhantomSpec, device: int = 0, out=None, out_host=None):
         fm = np.empty((n, n, n), np.float32) if spec.has_fieldmap else None
     _ck(lib, lib.swk_phantom_generate(int(device), C.byref(cs), mask.ctypes.data, None if fm is None else fm.ctypes.data, 0, C.byref(st)))
     return mask, fm, fov, st.asdict()
+
+
+def generate_mesh(fov_um: float, resolution: int, vertices, faces, device: int = 0):
+    """`spinwalk phantom -p`: mask of a closed triangle mesh centred in the FoV (≙ phantom::ply::run, src/phantom/phantom_ply.cpp:141-227).
+    vertices float64 [nv,3] in the PLY file's unit (mm), faces [nf,3].  Returns (mask uint8 [n,n,n], fov_m float32[3], stats dict)."""
+    lib = L.load()
+    v = np.ascontiguousarray(vertices, np.float64).reshape(-1, 3)
+    f = np.ascontiguousarray(faces, np.uint64).reshape(-1, 3)
+    n = int(resolution)
+    mask = np.empty((n, n, n), np.uint8)
+    st = L.PhantomStats()
+    _ck(lib, lib.swk_phantom_mesh(int(device), float(fov_um), n, v.ctypes.data, len(v), f.ctypes.data, len(f), mask.ctypes.data, 0, C.byref(st)))
+    fov = np.full(3, np.float32(fov_um) * np.float32(1e-6), np.float32)
+    return mask, fov, st.asdict()

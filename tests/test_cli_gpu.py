@@ -164,8 +164,8 @@ def test_cli_phantom_refusals(cli, tmp_path):
     assert r.returncode == 1 and "Phantom generation failed" in r.stderr and "too large" in r.stderr  # phantom_cylinder.cpp:87-91
     r = subprocess.run([cli, "phantom", "-c", "-z", "8", "-o", out], capture_output=True, text=True)
     assert r.returncode == 1 and "--fov is required" in r.stderr
-    r = subprocess.run([cli, "phantom", "-p", "-f", "10", "-z", "8", "-o", out], capture_output=True, text=True)
-    assert r.returncode == 1 and "ply" in r.stderr
+    r = subprocess.run([cli, "phantom", "-p", "-i", str(tmp_path / "missing.ply"), "-f", "10", "-z", "8", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 1 and "File does not exist" in r.stderr
     assert not os.path.exists(out)
 
 
@@ -202,3 +202,23 @@ def test_cli_whole_workflow_config_phantom_dwi_sim(cli, tmp_path):
     # same windows as tests/test_engine_gpu.py::test_fast_pgse_free_diffusion_known_answer (Monte-Carlo error of |S| ~ 2e-3 at 2e5 spins)
     assert abs(-slope / 1e-9 - 1.0) < 0.04, f"fitted D = {-slope:.3e}, a = {np.exp(intercept):.4f}, S = {sig}"
     assert abs(np.exp(intercept) - 1.0) < 0.015, f"fitted D = {-slope:.3e}, a = {np.exp(intercept):.4f}, S = {sig}"
+
+
+def test_cli_mesh_phantom(cli, tmp_path):
+    """`spinwalk phantom -p -i mesh.ply`: the file holds /mask, /fov and /bvf = 0 (the reference never fills the volume fraction of a mesh
+    phantom, phantom_ply.cpp:187) and no field map; the mask is the reference's (golden SHA-256)."""
+    import meshes
+
+    v, f = meshes.MESHES["torus"]()
+    ply = str(tmp_path / "torus.ply")
+    meshes.write_ply(ply, v, f, fmt="binary_little_endian", vertex_type="double", extra=True)
+    out = str(tmp_path / "mesh.h5")
+    r = subprocess.run([cli, "phantom", "-p", "-i", ply, "-f", "100", "-z", "37", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "576 triangles" in r.stdout and "Done." in r.stdout
+    assert sorted(h5util.names(out)) == ["bvf", "fov", "mask"]
+    gold = np.load(os.path.join(h5util.ROOT, "tests", "golden", "phantom", "mesh_torus.npz"))
+    assert _sha(h5util.read(out, "mask")) == str(gold["sha256_37"])
+    assert h5util.read(out, "bvf").ravel()[0] == 0.0
+    r = subprocess.run([cli, "phantom", "-p", "-f", "100", "-z", "37", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 1 and "--ply needs --ply_file" in r.stderr

@@ -152,3 +152,37 @@ def test_generator_random_specs_bit_exact(pg, pp, monkeypatch):
             continue
         assert_same(mask, fm, st, pp.oracle(**kw))
         done += 1
+
+
+# ---- triangle-mesh phantom (`spinwalk phantom -p`, swk_phantom_mesh) ----
+
+def test_mesh_phantom_bit_exact_vs_oracle_and_reference_golden(pg, pp):
+    import meshes
+
+    for name, make in sorted(meshes.MESHES.items()):
+        v, f = make()
+        gold = np.load(os.path.join(GOLD, "mesh_" + name + ".npz"))
+        for fov, res in ((60.0, 24), (100.0, 37), (45.0, 65)):
+            mask, fov_m, st = pg.generate_mesh(fov, res, v, f)
+            want = pp.oracle_mesh(fov, res, v, f)
+            assert np.array_equal(mask, want), (name, fov, res, int(mask.sum()), int(want.sum()))
+            assert st["n_shapes"] == len(f) and st["n_launches"] == 1
+            assert np.float32(st["volume_fraction"]) == np.float32(want.sum() * 100.0 / want.size)
+            if f"sha256_{res}" in gold:
+                assert digest(mask) == str(gold[f"sha256_{res}"])
+            assert np.array_equal(fov_m, np.full(3, np.float32(fov) * np.float32(1e-6), np.float32))
+
+
+def test_mesh_phantom_degenerate_inputs(pg, pp):
+    import meshes
+
+    v, f = meshes.box()
+    # no triangles: every voxel is outside the (empty) bounding box
+    mask, _, st = pg.generate_mesh(50.0, 16, v, f[:0])
+    assert mask.sum() == 0 and st["n_shapes"] == 0
+    # a mesh larger than the FoV: only the part inside is sampled, like the reference (no clipping of the mesh)
+    big = v * 0.2  # 200 um box in a 50 um FoV
+    mask, _, _ = pg.generate_mesh(50.0, 16, big, f)
+    assert np.array_equal(mask, pp.oracle_mesh(50.0, 16, big, f)) and mask.all()
+    with pytest.raises(pg.PhantomError, match="out of range"):
+        pg.generate_mesh(50.0, 16, v, f + np.uint64(5))
