@@ -142,3 +142,39 @@ def sphere_lattice_phantom(n: int, fov_um: float, cell_um: float = 40.0, vf_pct:
         mask[sx] = (dx * dx + dy * dy + dz * dz <= rr * rr).astype(np.uint8)
     fov_m = np.full(3, fov_um, np.float32) * np.float32(1e-6)
     return mask, None, fov_m
+
+
+def icosphere_mesh(subdiv: int = 5, radius_mm: float = 0.2):
+    """A closed triangle mesh (subdivided icosahedron) as `spinwalk phantom -p` input: (vertices float64 [nv,3] in mm, faces uint64 [nf,3]),
+    20 * 4**subdiv triangles.  Synthetic bench / test input."""
+    t = (1.0 + 5 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = np.asarray([(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+                    (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)], np.int64)
+    v = np.asarray(v, np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    for _ in range(subdiv):
+        edges = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
+        uniq, inv = np.unique(edges, axis=0, return_inverse=True)
+        mid = v[uniq[:, 0]] + v[uniq[:, 1]]
+        mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        m = inv.reshape(3, -1) + len(v)  # midpoint index of edges ab, bc, ca of every face
+        v = np.concatenate([v, mid])
+        a, b, c = f[:, 0], f[:, 1], f[:, 2]
+        ab, bc, ca = m[0], m[1], m[2]
+        f = np.concatenate([np.stack([a, ab, ca], 1), np.stack([b, bc, ab], 1), np.stack([c, ca, bc], 1), np.stack([ab, bc, ca], 1)])
+    return v * radius_mm, f.astype(np.uint64)
+
+
+def write_ply(path: str, vertices, faces) -> None:
+    """binary_little_endian PLY (double x/y/z, int vertex_indices) — the file `spinwalk phantom -p -i` reads."""
+    v = np.ascontiguousarray(vertices, "<f8")
+    f = np.ascontiguousarray(faces, np.int64)
+    rec = np.zeros(len(f), dtype=[("n", "u1"), ("i", "<i4", 3)])
+    rec["n"] = 3
+    rec["i"] = f
+    with open(path, "wb") as o:
+        o.write((f"ply\nformat binary_little_endian 1.0\nelement vertex {len(v)}\nproperty double x\nproperty double y\nproperty double z\n"
+                 f"element face {len(f)}\nproperty list uchar int vertex_indices\nend_header\n").encode())
+        o.write(v.tobytes())
+        o.write(rec.tobytes())
