@@ -142,3 +142,15 @@ def test_ini_writer_equals_mini_on_random_documents(tmp_path):
         with open(pa, "rb") as fa, open(pb, "rb") as fb:
             a, b = fa.read(), fb.read()
         assert a == b, f"trial {trial}: pretty={pretty}\nINPUT:\n{text!r}\nEDITS: {ops}\nmINI:\n{a!r}\nours:\n{b!r}"
+
+
+def test_reference_config_creation(tmp_path):
+    """The reference's own test (tests/test_config.cpp:36-62): generate_gre(TE = 12345, timestep = 25, two phantoms) writes gre.ini and
+    default_config.ini next to it; TE and TIME_STEP read back."""
+    out = str(tmp_path / "spinwalk_test" / "gre.ini")
+    assert our_config("gre", 12345, 25, ["phantom1.h5", "phantom2.h5"], out)
+    parent = str(tmp_path / "spinwalk_test" / "default_config.ini")
+    assert os.path.exists(out) and os.path.exists(parent)
+    kv = dict(line.split(" = ", 1) for line in open(out).read().splitlines() if " = " in line)
+    assert int(kv["TE"]) == 12345 and int(kv["TIME_STEP"]) == 25 and kv["PARENT_CONFIG"] == parent
+    assert kv["PHANTOM[0]"] == "phantom1.h5" and kv["PHANTOM[1]"] == "phantom2.h5"

@@ -186,3 +186,25 @@ def test_mesh_phantom_degenerate_inputs(pg, pp):
     assert np.array_equal(mask, pp.oracle_mesh(50.0, 16, big, f)) and mask.all()
     with pytest.raises(pg.PhantomError, match="out of range"):
         pg.generate_mesh(50.0, 16, v, f + np.uint64(5))
+
+
+# ---- the reference's own phantom tests (tests/test_phantom.cpp:17-34), on the GPU generator ----
+
+def test_reference_cylinder_creation(pg, pp):
+    """BOOST_AUTO_TEST_CASE(cylinder_creation): cylinder(600, 300, 0.11e-6, -1, -20, vf = 10, orientation 0, seed 10).run(false); |actual - vf| < 2."""
+    kw = dict(shape=0, fov_um=600.0, resolution=300, dchi=0.11e-6, Y=-1.0, radius_um=-20.0, volume_fraction=10.0, orientation_deg=0.0, seed=10)
+    mask, fm, _, st = pg.generate(spec_of(pg, kw))
+    assert fm is None and mask.shape == (300, 300, 300)
+    assert abs(st["volume_fraction"] - 10.0) < 2.0
+    want = pp.oracle(**kw)
+    assert np.array_equal(mask, want.mask) and np.float32(st["volume_fraction"]) == np.float32(want.bvf)
+
+
+def test_reference_sphere_creation(pg, pp):
+    """BOOST_AUTO_TEST_CASE(sphere_creation): sphere(600, 300, 0.11e-6, -1, -20, vf = 12, seed 0).run(false); |actual - vf| < 2."""
+    kw = dict(shape=1, fov_um=600.0, resolution=300, dchi=0.11e-6, Y=-1.0, radius_um=-20.0, volume_fraction=12.0, seed=0)
+    mask, fm, _, st = pg.generate(spec_of(pg, kw))
+    assert fm is None
+    assert abs(st["volume_fraction"] - 12.0) < 2.0
+    want = pp.oracle(**kw)
+    assert np.array_equal(mask, want.mask) and np.float32(st["volume_fraction"]) == np.float32(want.bvf)
