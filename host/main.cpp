@@ -33,7 +33,7 @@ void usage()
             "           -d,--dchi [0.11e-6]  -y,--oxy_level [0.75]  -e,--seed [-1]  -o,--output (required)  [--device N]\n"
             "  config   -s,--seq_name GRE|SE|bSSFP  -p,--phantoms FILE...  -e,--TE us  -t,--timestep us  -o,--output FILE\n"
             "  dwi      -b,--bvalue B...  -v,--bvector X Y Z  -d,--delta START delta DELTA (ms)  -c,--config FILE\n"
-            "  -g,--gpu_info  print the number of GPUs\n");
+            "  -g,--gpu_info  print GPU information\n");
 }
 
 // values following an option, up to the next option (negative numbers are values)
@@ -265,8 +265,10 @@ int main(int argc, char **argv)
     for (a.i = 1; a.i < argc; a.i++) {
         const std::string o = argv[a.i];
         if (o == "-g" || o == "--gpu_info") {
-            printf("Number of GPU(s): %d\n", swk_device_count());
-            if (a.i + 1 == argc) return 0;
+            char info[1024]; // ≙ callback_gpu_info: print_device_info(); exit(0) (src/spinwalk.cpp:50-51)
+            swk_device_info(info, sizeof info);
+            fputs(info, stdout);
+            return 0;
         } else if (o == "-l" || o == "--log") { if (a.i + 1 < argc) a.i++; } // log file of the reference CLI: messages go to stdout/stderr here
         else if (o == "-h" || o == "--help") { usage(); return 0; }
         else if (o == "-v" || o == "--version") { printf("spinwalk (B200 engine) %d.%d\n", SWK_VERSION_MAJOR, SWK_VERSION_MINOR); return 0; }

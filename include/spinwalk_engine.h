@@ -111,6 +111,9 @@ void        swk_destroy(swk_engine *e);
 const char *swk_last_error(const swk_engine *e); /* e may be NULL: error of the last failed swk_create */
 int         swk_version(void);                   /* major*100 + minor */
 int         swk_device_count(void);              /* ≙ sim::get_device_count, device_helper.cu; <=0 if none */
+/* ≙ sim::print_device_info (device_helper.cu:47-75, the `-g` flag): the same lines — driver / runtime CUDA versions, device count,
+ * name, compute capability, free and total memory of the current device — written into buf (NUL-terminated, truncated to n). */
+int         swk_device_info(char *buf, size_t n);
 
 /* ---- parameters::prepare (simulation_parameters.cuh:227-245) for callers that hold raw INI values ----
  * Fills p->c, p->s, p->n_timepoints, resolves n_dummy_scan < 0, converts diffusivity_m2s[n] -> sigma_out[n]. */

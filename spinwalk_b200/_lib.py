@@ -75,6 +75,7 @@ SYMBOLS = {
     "swk_last_error": (C.c_char_p, [_P]),
     "swk_version": (C.c_int, []),
     "swk_device_count": (C.c_int, []),
+    "swk_device_info": (C.c_int, [C.c_char_p, C.c_size_t]),
     "swk_prepare": (C.c_int, [C.POINTER(Params), C.c_float, C.c_float, _P, C.c_uint32, _P]),
     "swk_set_phantom": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "swk_set_sequence": (C.c_int, [_P, C.POINTER(Params), C.POINTER(Tables)]),

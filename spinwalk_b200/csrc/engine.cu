@@ -253,6 +253,32 @@ int swk_device_count(void)
     return n;
 }
 
+int swk_device_info(char *buf, size_t n)
+{
+    if (!buf || n == 0) return SWK_ERR_INVALID;
+    auto version = [](int v) { return std::to_string(v / 1000) + "." + std::to_string((v % 100) / 10); }; // device_helper.cu:41-45
+    std::string out;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess) out = std::string("Error: ") + cudaGetErrorString(err) + "\n";
+    else {
+        int rt = 0, drv = 0, dev = 0;
+        cudaRuntimeGetVersion(&rt);
+        cudaDriverGetVersion(&drv);
+        out += "The latest version of CUDA supported by the driver: " + version(drv) + ", current CUDA version: " + version(rt) + "\n";
+        out += "Number of devices: " + std::to_string(count) + "\n";
+        cudaDeviceProp prop{};
+        size_t free_b = 0, total_b = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            out += std::string(prop.name) + "\n";
+            out += "-Compute Capability: " + std::to_string(prop.major) + "." + std::to_string(prop.minor) + "\n";
+            out += "-Free GPU Memory: " + std::to_string(free_b >> 20) + " MB (out of " + std::to_string(total_b >> 20) + " MB)\n";
+        }
+    }
+    snprintf(buf, n, "%s", out.c_str());
+    return err == cudaSuccess ? SWK_OK : SWK_ERR_CUDA;
+}
+
 const char *swk_last_error(const swk_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
 int swk_create(int device_id, swk_engine **out)
