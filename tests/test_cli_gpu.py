@@ -222,3 +222,11 @@ def test_cli_mesh_phantom(cli, tmp_path):
     assert h5util.read(out, "bvf").ravel()[0] == 0.0
     r = subprocess.run([cli, "phantom", "-p", "-f", "100", "-z", "37", "-o", out], capture_output=True, text=True)
     assert r.returncode == 1 and "--ply needs --ply_file" in r.stderr
+
+
+def test_cli_gpu_info(cli):
+    """`spinwalk -g`: the lines of sim::print_device_info (device_helper.cu:47-75), then exit 0 (src/spinwalk.cpp:50-51)."""
+    r = subprocess.run([cli, "-g"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for must in ("The latest version of CUDA supported by the driver:", "Number of devices:", "-Compute Capability: 10.0", "-Free GPU Memory:"):
+        assert must in r.stdout, r.stdout
