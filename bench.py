@@ -595,8 +595,10 @@ def main():
     try:  # DRAM bytes per launch of this very workload from the committed ncu capture (profiles/traffic.json)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         ent = tj.get(f"{args.workload}:{args.mode}")
-        if ent and not args.spins and not args.scales:
-            traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+        if ent and not args.scales and (not args.spins or ent.get("spins_per_gpu")):
+            # a capture taken with fewer spins scales linearly (every spin does the same work on average)
+            traffic = ent["dram_bytes_per_launch"] * (S_per_gpu / ent["spins_per_gpu"] if ent.get("spins_per_gpu") else 1.0)
+            traffic_src = ent["source"]
     except Exception:
         pass
     per_pass_bytes = (st_counts["mask_gathers"] * 1 + st_counts["field_gathers"] * 4
@@ -608,6 +610,9 @@ def main():
               "frac_of_random_gather_peak": (fetches_per_s / probe["gathers_per_s"]) if probe.get("gathers_per_s") else None,
               "table_bytes": probe.get("table_bytes"),
               "hbm_64B_fetches_per_s": (traffic / 64 / (ker_ms_per_launch * 1e-3)) if traffic else None,
+              # the probe's own HBM rate: its gathers minus the share a uniformly random access finds in L2 (L2 bytes / table bytes)
+              "hbm_fetch_frac_of_probe": (traffic / 64 / (ker_ms_per_launch * 1e-3) / (probe["gathers_per_s"] * max(0.05, 1.0 - 126e6 / probe["table_bytes"])))
+              if (traffic and probe.get("gathers_per_s") and probe.get("table_bytes")) else None,
               "note": "random_gather_peak = swk_probe_gather: dependent random 4-byte gathers over the same voxel table, nothing else "
                       "(HBM row-activation bound, DESIGN.md §5); voxel_fetches include L1/L2 hits of the larger FoV scales"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
