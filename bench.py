@@ -117,6 +117,25 @@ def make_positions(S, fov, seed, first=0):
     return x * (np.float32(0.98) * f) + np.float32(0.01) * f
 
 
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """Only the JSON line may reach stdout: file descriptor 1 is pointed at stderr for everything else this process or its libraries
+    print (NCCL's version banner goes straight to fd 1), and emit() writes to the saved original."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -274,11 +293,11 @@ def mesh_bench(args):
             if i >= args.warmup:
                 ts.append(time.perf_counter() - t0)
         val = nc ** 3 * len(ts) / sum(ts)
-        print(json.dumps({"impl": "reference", "metric": "voxels/s", "value": val, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        emit({"impl": "reference", "metric": "voxels/s", "value": val, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
                           "config": {"workload": desc}, "gpu_launches": 0,
                           "cpu_baseline": {"value": val, "unit": "voxels/s", "cores": 1, "kind": "reference", "sample": f"the same mesh at {nc}^3 voxels"},
-                          "e2e": {"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
     import torch
 
@@ -326,7 +345,7 @@ def mesh_bench(args):
                                         "sample": f"the same mesh at {nc}^3 voxels with the reference's phantom::ply (its std::execution::par_unseq loop runs serially without TBB): {sec:.1f} s"}
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "voxels/s", "cores": 1, "kind": "reference", "sample": f"failed: {ex}"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def phantom_bench(args):
@@ -348,11 +367,11 @@ def phantom_bench(args):
             if i >= args.warmup:
                 ts.append(time.perf_counter() - t0)
         v = V * len(ts) / sum(ts)
-        print(json.dumps({"impl": "reference", "metric": "voxels/s", "value": v, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        emit({"impl": "reference", "metric": "voxels/s", "value": v, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
                           "data": "synthetic", "config": {"workload": desc}, "gpu_launches": 0,
                           "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "reference", "sample": "the whole phantom"},
-                          "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
     import torch
 
@@ -431,7 +450,7 @@ def phantom_bench(args):
                 line["cpu_baseline"] = {"value": n * n * zw[1] / sec, "unit": "voxels/s", "cores": 1, "kind": "port", "sample": f"z slices [0, {zw[1]}) of the phantom: {sec:.1f} s"}
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -447,6 +466,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    protect_stdout()
     if args.workload == "ph-mesh":
         return mesh_bench(args)
     if args.workload in PHANTOM_RECIPES:
@@ -475,12 +495,12 @@ def main():
         tot_sec = sum(v[1] for v in vals)
         v = tot_steps / tot_sec
         samples["value"] = v
-        print(json.dumps({"impl": "reference", "metric": "spin-steps/s", "value": v, "unit": "spin-steps/s", "n_gpus": args.gpus,
+        emit({"impl": "reference", "metric": "spin-steps/s", "value": v, "unit": "spin-steps/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / max(1, args.steps),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
                           "data": "synthetic", "config": {"workload": desc, "note": "each step = bounded sample of the workload on host cores"},
                           "cpu_baseline": samples, "gpu_launches": 0,
-                          "e2e": {"value": v, "unit": "spin-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": "spin-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -495,7 +515,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     mode = sw.MODE_FAST if args.mode == "fast" else sw.MODE_COMPAT
@@ -654,7 +673,7 @@ def main():
         except Exception as ex:
             line["reference_cuda"] = {"value": None, "sample": f"failed: {ex}"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
