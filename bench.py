@@ -420,7 +420,7 @@ def phantom_bench(args):
             "e2e": {"value": V * args.steps / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": out_bytes, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "api": "swk_phantom_generate (C-ABI) with pageable host buffers: placement + voxel fill + D2H of mask and field map"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "swk::phantom::slab_broadcast_kernel" if kw["shape"] == 0 else "swk::phantom::sphere_fill_kernel",
+                         "kernel": "swk::phantom::slab_broadcast_bulk_kernel" if kw["shape"] == 0 else "swk::phantom::sphere_fill_kernel",
                          "algorithmic_bytes_per_launch": out_bytes, "kernel_ms_per_launch": ker_ms / args.steps,
                          "note": "5 B written per voxel (1 B mask + 4 B field) or 1 B without field map; the sphere kernel is bound by two IEEE double "
                                  "divisions per (voxel, sphere) pair, not by HBM"}}
