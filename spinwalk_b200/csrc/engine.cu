@@ -882,6 +882,9 @@ int swk_run(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_fir
     // Large runs are cut into <= 8 slices of >= 2^21 spins so that the device-to-host copy of slice i overlaps the walk of slice
     // i+1 (measured on C2: 4 slices cost 0.5 % each in kernel time and leave 1/4 of the 0.24 s download exposed).
     uint32_t n_slices = (M1 || XYZ1 || T) ? std::min<uint32_t>(8u, std::max<uint32_t>(1u, n_local >> 21)) : 1u;
+    // Long runs (bSSFP: 220 200 steps per walker) stay in one piece: their download is < 1 % of the walk (a walker's 25 output bytes
+    // cost what ~160 steps cost), and only an unsliced run pauses for re-binning (run_impl) — C4: 1.56e11 sliced vs 2.15e11 spin-steps/s.
+    if (e->has_sequence && !e->P.record_trajectory && (uint64_t)e->P.n_timepoints * (uint64_t)(e->P.n_dummy_scan + 1) >= 16000u) n_slices = 1;
     if (const char *ev = getenv("SWK_SLICES")) n_slices = std::max(1, atoi(ev)); // tuning knob
     HostOut host;
     host.M1 = M1; host.XYZ1 = XYZ1; host.T = T;

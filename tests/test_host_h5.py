@@ -6,13 +6,17 @@ No libhdf5 / h5py exists in this toolchain, so the codec is pinned two ways:
     (scipy/io/matlab/tests: testdouble = 0 : pi/4 : 2 pi);
   * the WRITER through the reader (round trips of every type / rank, many datasets => several symbol-table nodes) and
     through byte-level checks of the structures libhdf5 validates when it opens a file (signature, end-of-file address,
-    sorted symbol table, B-tree keys, heap names)."""
+    sorted symbol table, B-tree keys, heap names);
+  * a SECOND, independent parser (tests/h5spec.py: pure Python, written from the format specification, strict about every
+    reserved byte, alignment, key interval and message count libhdf5 enforces) that is itself pinned on the libhdf5-written file
+    and must accept, and decode identically, everything the Writer emits."""
 import os
 import struct
 
 import numpy as np
 import pytest
 
+import h5spec
 import h5util
 
 
@@ -114,3 +118,76 @@ def test_reader_errors(tmp_path):
     trunc.write_bytes(open(q, "rb").read()[:-4])
     with pytest.raises(RuntimeError, match="past the end"):
         h5util.read(str(trunc), "a")
+
+
+def test_independent_parser_reads_the_libhdf5_written_file():
+    """pins tests/h5spec.py itself: user block of 512 bytes, base address 512, absolute end-of-file address, v2 layout message."""
+    p = _scipy_mat()
+    if p is None:
+        pytest.skip("scipy's MATLAB v7.3 sample is not installed")
+    f = h5spec.File(p)
+    assert (f.user_block, f.base, f.eof) == (512, 512, os.path.getsize(p)) and list(f.links) == ["testdouble"]
+    v = f.dataset("testdouble")
+    assert v.dtype == np.dtype("<f8") and v.shape == (9, 1) and np.allclose(v[:, 0], np.arange(9) * np.pi / 4, rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("n_datasets", [0, 1, 8, 9, 17, 40, 64, 256])
+def test_writer_output_passes_the_independent_parser(tmp_path, n_datasets):
+    """every file structure of the Writer (1 .. 32 symbol-table nodes under one B-tree node, all ten element types, ranks 1-4)
+    is accepted by the strict parser and decodes to the arrays that were written."""
+    rng = np.random.default_rng(100 + n_datasets)
+    ds = {}
+    for i in range(n_datasets):
+        dt = h5util.DTYPES[i % len(h5util.DTYPES)]
+        shape = tuple(int(x) for x in rng.integers(1, 6, size=1 + i % 4))
+        ds[f"{'ZMa_'[i % 4]}{i:03d}{'y' * (i % 9)}"] = (rng.standard_normal(shape) * 100).astype(dt)
+    p = str(tmp_path / "w.h5")
+    h5util.write(p, ds)
+    f = h5spec.File(p)
+    assert sorted(f.links) == sorted(ds) and f.base == 0 and f.eof == os.path.getsize(p)
+    for k, v in ds.items():
+        a = f.dataset(k)
+        assert a.dtype == v.dtype and a.shape == v.shape and np.array_equal(a, v), k
+
+
+def test_reference_file_layouts_pass_the_independent_parser(tmp_path):
+    """the phantom file (phantom_base.cpp:72-105) and the sim output file (monte_carlo.cu:168-197) as this host writes them."""
+    rng = np.random.default_rng(7)
+    ph = {"mask": (rng.random((7, 5, 6)) < 0.2).astype(np.uint8), "fieldmap": rng.standard_normal((7, 5, 6)).astype(np.float32),
+          "fov": np.array([7e-6, 5e-6, 6e-6], np.float32), "bvf": np.array([20.0], np.float32)}
+    K, S, E = 2, 13, 3
+    out = {"M": rng.standard_normal((K, S, E, 3)).astype(np.float32), "XYZ": rng.standard_normal((K, S, 1, 3)).astype(np.float32),
+           "T": rng.integers(0, 2, (K, S, E, 1)).astype(np.uint8), "scales": np.ones((K, 1, 1, 1), np.float32), "TE": np.full((E, 1, 1, 1), 0.02, np.float32)}
+    for name, ds in (("phantom.h5", ph), ("out.h5", out)):
+        p = str(tmp_path / name)
+        h5util.write(p, ds)
+        f = h5spec.File(p)
+        assert sorted(f.links) == sorted(ds)
+        for k, v in ds.items():
+            assert np.array_equal(f.dataset(k), v) and f.dataset(k).dtype == v.dtype
+
+
+def test_independent_parser_rejects_what_libhdf5_rejects(tmp_path):
+    """the second opinion is only worth something if it is strict: flip the fields libhdf5 validates and expect a refusal."""
+    p = str(tmp_path / "ok.h5")
+    h5util.write(p, {"a": np.arange(6, dtype=np.float32).reshape(2, 3), "b": np.arange(4, dtype=np.int16)})
+    good = bytearray(open(p, "rb").read())
+    h5spec.File(p)
+
+    def broken(edit):
+        b = bytearray(good)
+        edit(b)
+        q = tmp_path / "bad.h5"
+        q.write_bytes(bytes(b))
+        with pytest.raises(h5spec.FormatError):
+            f = h5spec.File(str(q))
+            for k in f.links:
+                f.dataset(k)
+
+    root_oh = struct.unpack_from("<Q", good, 64)[0]
+    broken(lambda b: struct.pack_into("<Q", b, 40, len(b) + 8))           # end-of-file address beyond the file
+    broken(lambda b: struct.pack_into("<H", b, root_oh + 2, 2))           # message count of the root object header
+    broken(lambda b: b.__setitem__(slice(root_oh + 40, root_oh + 44), b"XXXX"))  # B-tree signature (the node follows the 40-byte header)
+    a_oh = h5spec.File(p).links["a"]
+    broken(lambda b: b.__setitem__(a_oh + 21, 1))                         # reserved byte of a message header
+    broken(lambda b: struct.pack_into("<I", b, a_oh + 8, 100))            # header size not matching its messages
