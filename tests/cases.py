@@ -122,8 +122,51 @@ def stuck(n_spins=256):
     return c, mask, None, fov, _xyz0(c, fov)
 
 
+def ragged(n_spins=257):
+    """ragged launch (one spin more than a block) on a tiny anisotropic 3 x 5 x 7 phantom whose FoV is a few step lengths wide:
+    every spin wraps around the periodic FoV many times (CROSS_FOV=1), half-permeable interface, two echoes."""
+    mask = np.zeros((3, 5, 7), np.uint8)
+    mask[1, 1:4, 2:6] = 1
+    rng = np.random.default_rng(11)
+    fm = (rng.standard_normal(mask.shape) * 5e-8).astype(np.float32)
+    fov = np.array([3e-6, 5e-6, 7e-6], np.float32)
+    c = po.Case(fov=tuple(fov), phantom_size=mask.shape, n_spins=n_spins, TR_us=10000, TE_tp=[60, 199], timestep_us=50, cross_fov=1,
+                pXY=[1.0, 0.5, 0.5, 1.0], T2_ms=[41.0, 25.0], scales=[0.3, 1.0, 2.5], seed=5)
+    return c, mask, fm, fov, _xyz0(c, fov)
+
+
+def single():
+    """one spin: the smallest input the reference accepts (NUMBER_OF_SPINS = 1)."""
+    return ragged(n_spins=1)
+
+
+def events_edge(n_spins=200):
+    """event tables at their edges: echoes at timepoint 0, at the last timepoint and beyond the TR (never fires: its slot stays 0);
+    RF, dephasing, gradient and echo on one timepoint; gradient samples at timepoint 0, in runs of two and next to the end of the TR;
+    RF phases on the exact fast paths of xrot_withphase (180, 270, -90; kernels.cuh:160-195), flip angles > 180 and < 0;
+    two dummy scans; gradient scaling with a zero and a negative scale."""
+    mask, fm, fov = _cyl()
+    c = po.Case(fov=tuple(fov), phantom_size=mask.shape, n_spins=n_spins, TR_us=10000, timestep_us=50, n_dummy_scan=2,
+                TE_tp=[0, 57, 199, 230], RF_FA_deg=[45.0, 200.0, -30.0], RF_PH_deg=[180.0, 270.0, -90.0], RF_tp=[0, 57, 100],
+                dephasing_deg=[33.0, 720.0], dephasing_tp=[57, 199],
+                gradient_tp=[0, 1, 57, 58, 59, 198, 199], gradX_mTm=[5.0, -3.0, 2.0, 4.0, 4.0, 1.0, -6.0],
+                gradY_mTm=[0.0, 1.0, 0.0, -2.0, 2.0, 0.0, 0.5], gradZ_mTm=[1.0, 1.0, 1.0, 0.0, 0.0, -1.0, 3.0],
+                scales=[0.0, 1.0, -2.0], scale_type=po.SCALE_GRADIENT, T1_ms=[300.0, 500.0], T2_ms=[41.0, 60.0], seed=31, B0=3.0)
+    return c, mask, fm, fov, _xyz0(c, fov)
+
+
+def frozen(n_spins=300):
+    """DIFFUSIVITY = 0 in one substrate behind permeable walls: a spin that enters a vessel stops drawing random numbers for good
+    (kernels.cu:130 skips the draws when sigma == 0) and keeps accruing the phase of the voxel it froze in."""
+    mask, fm, fov = _cyl()
+    c = po.Case(fov=tuple(fov), phantom_size=mask.shape, n_spins=n_spins, TR_us=20000, TE_tp=[150, 399], diffusivity=[1e-9, 0.0],
+                pXY=[1.0, 1.0, 1.0, 1.0], T2_ms=[41.0, 20.0], scales=[0.2, 1.0], seed=13)
+    return c, mask, fm, fov, _xyz0(c, fov)
+
+
 ALL = dict(gre=gre, se=se, pgse=pgse, ssfp=ssfp, multi_echo=multi_echo, trajectory=trajectory,
-           gradient_rng_free=gradient_rng_free, stuck=stuck)
+           gradient_rng_free=gradient_rng_free, stuck=stuck, ragged=ragged, single=single, events_edge=events_edge,
+           frozen=frozen)
 
 
 def to_simconfig(c: po.Case):

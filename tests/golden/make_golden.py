@@ -1,6 +1,6 @@
 """Generates tests/golden/<case>_<flavour>.npz from the UNMODIFIED reference (oracle/_ref, built by
 `make -C oracle ref` from /root/reference/src/sim/kernels.cu).  Run in the container that has /root/reference:
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]      (no names: every case of tests/cases.py)
 Each file records the toolchain, the seeded inputs (xyz0) and the reference outputs M1 / XYZ1 / T."""
 import os
 import platform
@@ -20,6 +20,8 @@ tool = "g++ " + subprocess.run(["g++", "-dumpfullversion"], capture_output=True,
        "; nvcc " + subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout.strip().split("release ")[-1].split(",")[0] + \
        "; " + platform.platform()
 for name, fn in cases.ALL.items():
+    if len(sys.argv) > 1 and name not in sys.argv[1:]:
+        continue
     case, mask, fm, fov, xyz0 = fn()
     for flavour, tag in ((po.RNG_MT19937, "mt19937"), (po.RNG_MINSTD, "minstd")):
         r = po.run_ref(case, fm, mask, xyz0, flavour=flavour)

@@ -76,7 +76,8 @@ def _ensemble(M1, T, sub=None):
     return m, np.sqrt(v / n), w.mean(axis=1)
 
 
-@pytest.mark.parametrize("name,n_spins", [("gre", 6000), ("se", 6000), ("pgse", 6000), ("ssfp", 2000), ("multi_echo", 6000)])
+@pytest.mark.parametrize("name,n_spins", [("gre", 6000), ("se", 6000), ("pgse", 6000), ("ssfp", 2000), ("multi_echo", 6000), ("events_edge", 5000),
+                                          ("frozen", 5000)])
 def test_fast_mode_ensemble_vs_oracle(sw, oracle, name, n_spins):
     """FAST mode (Philox + Box-Muller + FP32 grid coordinates) is a different random stream, so parity is
     statistical: per (scale, echo, component) |mean_fast - mean_oracle| <= 4.5 sqrt(SE_fast^2 + SE_oracle^2),
@@ -286,3 +287,47 @@ def test_rebinned_long_run_equals_uninterrupted_run(sw, oracle, monkeypatch, sca
     for key in ("steps", "mask_gathers", "field_gathers", "rejects", "lost"):
         assert st0[key] == st1[key], key
     assert st2["n_launches"] == 1
+
+
+@pytest.mark.parametrize("name", ["se", "multi_echo", "events_edge"])
+def test_fast_kernel_variants_agree(sw, name):
+    """The FAST walk has three voxel fetches (packed word / mask byte + FP32 field / mask only) and runs with or without the
+    locality order.  A lane's random stream depends on its own history only, so: unsorted == sorted bit for bit; the split
+    fetch (RUN_NO_PACK: the exact FP32 field instead of the packed word's 20 mantissa bits) walks the very same path (T and XYZ1
+    bitwise) and its magnetisation differs by the field rounding only (relative 2^-21 of the accrued phase)."""
+    case, mask, fm, fov, xyz0 = cases.ALL[name](n_spins=700)
+    cfg = cases.to_simconfig(case)
+    with sw.Engine(0) as e:
+        e.set_phantom(mask, fm, fov)
+        e.set_sequence(cfg)
+        e.set_spins(xyz0)
+        e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL)
+        base = e.download() + (e.sums(),)
+        e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_NO_SORT)
+        unsorted = e.download() + (e.sums(),)
+        e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_NO_PACK)
+        split = e.download() + (e.sums(),)
+        e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL)  # and back: the order and the packed table are rebuilt
+        again = e.download()
+    for a, b, c in zip(base[:3], unsorted[:3], again):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert np.allclose(base[3], unsorted[3], rtol=1e-9, atol=1e-3)  # sums: another summation order of the same FP32 values
+    assert np.array_equal(base[1], split[1]) and np.array_equal(base[2], split[2]), "the split fetch must walk the same path"
+    assert np.abs(base[0] - split[0]).max() <= 2e-4
+
+
+def test_single_spin_and_ragged_sizes(sw, oracle):
+    """sizes around the launch granularity (1, 255, 256, 257 spins; 256-thread blocks): the first spins of a larger population
+    give the same results whatever the population size, in both modes (the dephasing-free case does not depend on n_spins)."""
+    case, mask, fm, fov, xyz0 = cases.ragged(n_spins=257)
+    for mode in (sw.MODE_COMPAT, sw.MODE_FAST):
+        full = None
+        for n in (257, 256, 255, 1):
+            case.n_spins = n
+            got = _run_engine(sw, case, mask, fm, fov, xyz0[:n], mode)
+            assert got["M1"].shape == (3, n, 2, 3) and got["T"].shape == (3, n, 2)
+            if full is None:
+                full = got
+            else:
+                for k in ("M1", "XYZ1", "T"):
+                    assert np.array_equal(got[k], full[k][:, :n]), (mode, n, k)
