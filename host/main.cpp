@@ -122,6 +122,7 @@ int run_phantom(Args &a)
         }
         else if (o == "-o" || o == "--output") { if (!a.one(p.output)) return fail_usage("--output: a path is required"); }
         else if (o == "--device") { if (!a.one(v)) return fail_usage("--device: a number is required"); p.device = atoi(v.c_str()); }
+        else if (o == "-h" || o == "--help") { usage(); return 0; } // CLI11 gives every subcommand a help flag
         else return fail_usage("The following argument was not expected: " + o);
     }
     if (!have_fov) return fail_usage("--fov is required");
@@ -156,6 +157,7 @@ int run_config(Args &a)
         else if (o == "-e" || o == "--TE") { if (!a.one(v) || !to_u32(v, c.TE_us) || c.TE_us == 0) return fail_usage("--TE: Number less or equal to 0: " + v); have[2] = true; }
         else if (o == "-t" || o == "--timestep") { if (!a.one(v) || !to_u32(v, c.timestep_us) || c.timestep_us == 0) return fail_usage("--timestep: Number less or equal to 0: " + v); have[3] = true; }
         else if (o == "-o" || o == "--output") { if (!a.one(c.output)) return fail_usage("--output: a path is required"); have[4] = true; }
+        else if (o == "-h" || o == "--help") { usage(); return 0; } // CLI11 gives every subcommand a help flag
         else return fail_usage("The following argument was not expected: " + o);
     }
     const char *names[5] = {"--seq_name", "--phantoms", "--TE", "--timestep", "--output"};
@@ -204,7 +206,8 @@ int run_dwi(Args &a)
         } else if (o == "-c" || o == "--config") {
             if (!a.one(d.config)) return fail_usage("--config: a path is required");
             if (!std::filesystem::exists(d.config)) return fail_usage("--config: File does not exist: " + d.config);
-        } else return fail_usage("The following argument was not expected: " + o);
+        } else if (o == "-h" || o == "--help") { usage(); return 0; } // CLI11 gives every subcommand a help flag
+        else return fail_usage("The following argument was not expected: " + o);
     }
     if (!have_b) return fail_usage("--bvalue is required");
     if (!have_v) return fail_usage("--bvector is required");
@@ -242,7 +245,8 @@ int run_sim(Args &a)
             }
         } else if (o == "-c" || o == "--configs") {
             for (const auto &s : a.many()) configs.push_back(s);
-        } else return fail_usage("The following argument was not expected: " + o);
+        } else if (o == "-h" || o == "--help") { usage(); return 0; } // CLI11 gives every subcommand a help flag
+        else return fail_usage("The following argument was not expected: " + o);
     }
     if (configs.empty()) return fail_usage("--configs is required");
     for (const auto &c : configs)
