@@ -182,6 +182,13 @@ void swk_free_pinned(void *ptr);
 int swk_probe_gather(swk_engine *e, uint32_t threads_per_sm, uint32_t iters, double *gathers_per_s, uint64_t *table_bytes);
 
 /* ---- plumbing for callers that share the device with the engine (PyTorch, NCCL) ---- */
+/* Test hook: runs the random-number building blocks of SWK_MODE_FAST on caller-supplied inputs in[n][4], results in out[n][8].
+ *   which = 0: the Philox4x32-10 block of the displacement stream (fixed key 243F6A88 85A308D3), counter = in[i][0..3] -> 4 words;
+ *   which = 1: the Philox2x32-10 word of the permeability stream, counter = in[i][0..1], key = in[i][2] -> word, FP32 bits of its uniform [0,1);
+ *   which = 2: the six Box-Muller normals made from the 128-bit block in[i][0..3] -> 6 FP32 bit patterns (step order x y z, x y z).
+ * No counterpart in the reference (its generators are thrust::minstd_rand / std::mt19937, src/sim/kernels.cu:77-88). */
+int swk_debug_rng(swk_engine *e, int which, const uint32_t *in, uint32_t n, uint32_t *out);
+
 void    *swk_stream(swk_engine *e);            /* cudaStream_t the engine launches on                       */
 double  *swk_device_sums(swk_engine *e);       /* engine-owned device sums buffer of the last run, or NULL  */
 uint64_t swk_device_bytes(const swk_engine *e);/* device memory currently held (≙ get_total_memory)         */

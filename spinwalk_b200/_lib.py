@@ -92,6 +92,7 @@ SYMBOLS = {
     "swk_stream": (_P, [_P]),
     "swk_device_sums": (_P, [_P]),
     "swk_device_bytes": (C.c_uint64, [_P]),
+    "swk_debug_rng": (C.c_int, [_P, C.c_int, _P, C.c_uint32, _P]),
     # include/spinwalk_phantom.h
     "swk_phantom_shapes": (C.c_int, [C.POINTER(PhantomSpec), _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "swk_phantom_generate": (C.c_int, [C.c_int, C.POINTER(PhantomSpec), _P, _P, C.c_int, C.POINTER(PhantomStats)]),

@@ -224,6 +224,33 @@ __global__ void rebin_keys_kernel(const uint32_t *state_vox, const uint4 *state_
     ids[i] = (uint32_t)(i % n_local);
 }
 
+// key of the permeability stream (walk_fast.cuh philox2x32_10): a 32-bit fold of the run's seed
+uint32_t perm_stream_key(uint64_t seed) { return (uint32_t)seed + 0x9E3779B9u * (uint32_t)(seed >> 32) + 0x7F4A7C15u; }
+
+// swk_debug_rng: the random-number building blocks of the FAST walk, run on caller-supplied inputs (tests/test_rng_gpu.py)
+__global__ void debug_rng_kernel(int which, const uint32_t *in, uint32_t n, uint32_t one_bits, uint32_t *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c0 = in[4 * (size_t)i], c1 = in[4 * (size_t)i + 1], c2 = in[4 * (size_t)i + 2], c3 = in[4 * (size_t)i + 3];
+    uint32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (which == 0) {
+        const uint4 r = philox_fixed(c0, c1, c2, c3);
+        o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+    } else if (which == 1) {
+        uint32_t key[10];
+        for (uint32_t r = 0; r < 10; r++) key[r] = c2 + r * 0x9E3779B9u;
+        o[0] = philox2x32_10(c0, c1, key);
+        o[1] = __float_as_uint(u01_open1(o[0]));
+    } else {
+        float a0, a1, a2, b0, b1, b2;
+        normals6_fast(make_uint4(c0, c1, c2, c3), one_bits, a0, a1, a2, b0, b1, b2);
+        o[0] = __float_as_uint(a0); o[1] = __float_as_uint(a1); o[2] = __float_as_uint(a2);
+        o[3] = __float_as_uint(b0); o[4] = __float_as_uint(b1); o[5] = __float_as_uint(b2);
+    }
+    for (int k = 0; k < 8; k++) out[8 * (size_t)i + k] = o[k];
+}
+
 bool ascending(const int32_t *t, uint32_t n)
 {
     for (uint32_t i = 1; i < n; i++)
@@ -642,6 +669,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     A.cross_fov = e->P.cross_fov;
     A.record = e->P.record_trajectory;
     A.one_bits = 0x3f800000u;
+    for (uint32_t r = 0; r < 10; r++) A.perm_key[r] = perm_stream_key(e->P.seed) + r * 0x9E3779B9u;
     A.blob = static_cast<const uint8_t *>(e->blob.p);
     A.L = e->L;
     A.scales = static_cast<const float *>(e->scales.p);
@@ -938,6 +966,23 @@ int swk_probe_gather(swk_engine *e, uint32_t threads_per_sm, uint32_t iters, dou
     CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     *gathers_per_s = (double)grid * 256.0 * iters / (ms * 1e-3);
     if (table_bytes) *table_bytes = (uint64_t)n_words * 4;
+    return SWK_OK;
+}
+
+int swk_debug_rng(swk_engine *e, int which, const uint32_t *in, uint32_t n, uint32_t *out)
+{
+    if (!e) return SWK_ERR_INVALID;
+    if (!in || !out || n == 0 || which < 0 || which > 2) return fail(e, SWK_ERR_INVALID, "swk_debug_rng: bad arguments");
+    CK(cudaSetDevice(e->device));
+    DevBuf d_in, d_out;
+    struct Free { DevBuf &a, &b; ~Free() { release(a); release(b); } } guard{d_in, d_out};
+    int rc;
+    if ((rc = ensure(e, d_in, (size_t)n * 16)) != SWK_OK || (rc = ensure(e, d_out, (size_t)n * 32)) != SWK_OK) return rc;
+    CK(cudaMemcpyAsync(d_in.p, in, (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+    debug_rng_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(which, static_cast<const uint32_t *>(d_in.p), n, 0x3f800000u, static_cast<uint32_t *>(d_out.p));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out.p, (size_t)n * 32, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return SWK_OK;
 }
 

@@ -51,6 +51,23 @@ __device__ __forceinline__ uint4 philox_fixed(uint32_t c0, uint32_t c1, uint32_t
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Philox2x32-10 (same paper) for the permeability uniform (kernels.cu:154): one 32-bit word is needed per test, and the test runs
+// whenever ANY lane of the warp changes substrate with 0 < P < 1 — half the multiplies of a 4x32 block (10 IMAD.WIDE + 10 LOP3).
+//   counter = (attempt index of the walker, global spin id); key = a 32-bit fold of the run's seed (engine.cu), whose ten round keys
+//   key + r * 0x9E3779B9 arrive as kernel parameters, i.e. as constant-bank operands of the LOP3s.
+// A different generator AND key than the displacement stream: the two are independent (the reference draws both from copies of
+// one minstd stream).
+__device__ __forceinline__ uint32_t philox2x32_10(uint32_t c0, uint32_t c1, const uint32_t (&key)[10])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
+        c0 = hi ^ key[r] ^ c1;
+        c1 = lo;
+    }
+    return c0;
+}
+
 // three N(0,1) from 128 random bits: Box-Muller, 23-bit uniforms, hardware transcendental approximations.
 // |n| <= sqrt(2 ln 2^23) = 5.65 by construction (what bounds the fixed-point step below).
 __device__ __forceinline__ void normals3_fast(const uint4 r, float &n0, float &n1, float &n2)
@@ -259,7 +276,6 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
     uint32_t itr = 0;
     const uint32_t seed_lo = (uint32_t)A.seed;
     const uint32_t seed_hi_walk = ((uint32_t)(A.seed >> 32) & 0x3fffffffu) | (STREAM_WALK << 30);
-    const uint32_t seed_hi_perm = ((uint32_t)(A.seed >> 32) & 0x3fffffffu) | (STREAM_PERMEABILITY << 30);
     uint32_t st_mask = 0, st_field = 0, st_rej = 0, st_steps = 0; // per thread and launch: < 2^32
     bool lost = false;
 
@@ -342,10 +358,10 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
                 if (hop) { // kernels.cu:150-170
                     if (ts != ts_old) {
                         // accept iff u < P_XY[from][to], u in [0,1) (kernels.cu:154).  P <= 0 always rejects and P >= 1 always accepts:
-                        // the uniform (its own Philox stream, so skipping a draw changes nothing else) is only generated in between.
+                        // the uniform (its own Philox2x32 stream, so skipping a draw changes nothing else) is only generated in between.
                         const float pxy = tpXY[ts_old * L.n_sub + ts];
                         bool reject = pxy <= 0.f;
-                        if (pxy > 0.f && pxy < 1.f) reject = u01_open1(philox_fixed(perm_ctr, seed_lo, spin_no, seed_hi_perm).x) >= pxy;
+                        if (pxy > 0.f && pxy < 1.f) reject = u01_open1(philox2x32_10(perm_ctr, spin_no, A.perm_key)) >= pxy;
                         if (reject) {
                             if (STATS) st_rej++;
                             if (itr++ > A.max_iter) { alive = false; lost = true; rem = 0; }

@@ -63,6 +63,7 @@ struct WalkArgs {
     uint64_t seed, max_iter;
     int32_t  cross_fov, record;
     uint32_t one_bits;       // 0x3f800000 (FAST mode: a constant the compiler must keep in a register, walk_fast.cuh and_or)
+    uint32_t perm_key[10];   // FAST mode: round keys of the permeability stream (walk_fast.cuh philox2x32_10), key + r * 0x9E3779B9
     // sequence tables
     const uint8_t *blob;
     BlobLayout L;
