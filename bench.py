@@ -653,7 +653,8 @@ def main():
                        "l2": f"inputs larger than L2 (phantom {5 * ph['n'] ** 3 / 1e9:.2f} GB vs 126 MB)" if ph["n"] >= 600 else "phantom fits in L2; outputs (12.5 GB > L2) rewritten every pass",
                        "phantom": f"generated on the device by swk_generate_phantom: {gen['n_shapes']} shapes, volume fraction {gen['volume_fraction']:.3f} %, "
                                   f"voxel fill {gen['kernel_ms']:.2f} ms (bit-identical to the reference's `spinwalk phantom` for this recipe)",
-                       "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums"},
+                       "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums",
+                       **({"zslab": "SWK_ZSLAB=1: z-invariant phantom walked on its [nx][ny] slab (opt-in specialisation; the voxel table is then L1/L2-resident, NOT the default path and not the headline configuration)"} if os.environ.get("SWK_ZSLAB") else {})},
             "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": args.steps * st["n_launches"],
             "e2e": e2e, "roofline": roofline, "lost_spins": st_counts["lost"]}
 

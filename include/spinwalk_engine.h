@@ -145,7 +145,11 @@ enum { SWK_OUT_M1 = 1, SWK_OUT_XYZ1 = 2, SWK_OUT_T = 4, SWK_OUT_ALL = 7,
        SWK_RUN_STATS = 16,  /* count gathers / rejections (swk_stats); slightly slower kernel variant */
        SWK_RUN_NO_SORT = 32, /* simulate spins in caller order (no substrate/Morton locality order); for A/B tests */
        SWK_RUN_NO_PACK = 64, /* FAST mode: gather mask byte + FP32 field separately instead of the packed voxel word */
-       SWK_RUN_NO_REBIN = 128 /* FAST mode: never pause a long run (many TRs) to re-sort the spins by their current voxel; for A/B tests */ };
+       SWK_RUN_NO_REBIN = 128, /* FAST mode: never pause a long run (many TRs) to re-sort the spins by their current voxel; for A/B tests */
+       SWK_RUN_ZSLAB = 256 /* FAST mode, opt-in (also: environment SWK_ZSLAB=1): when mask and field map do not depend on z (checked on the device;
+                              every cylinder phantom of `spinwalk phantom -c`), fetch the packed voxel words from the [nx][ny] slab instead of
+                              the [nx][ny][nz] table — the same words, hence the same results bit for bit, from an L1/L2-resident table.
+                              Ignored (normal table) for any other phantom. */ };
 int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags,
                    double *d_sums);
 

@@ -60,6 +60,9 @@ struct swk_engine {
     // phantom
     DevBuf mask, fieldmap, packed;
     bool packed_valid = false;
+    DevBuf slab;            // SWK_RUN_ZSLAB: packed words of one z plane, [nx][ny]
+    bool slab_valid = false;
+    int z_invariant = -1;   // -1 not checked yet, 0 / 1: mask and field map do not depend on z
     uint64_t dims[3] = {0, 0, 0};
     float fov[3] = {0, 0, 0};
     uint32_t mask_substrates = 0;
@@ -174,6 +177,26 @@ __global__ void pack_voxels_kernel(const uint8_t *mask, const float *field, size
         uint32_t b = __float_as_uint(field[i]);
         if ((b & 0x7f800000u) != 0x7f800000u) b += 8u; // round to nearest (carry into the exponent is still the right value)
         out[i] = (b & 0xfffffff0u) | (uint32_t)mask[i];
+    }
+}
+
+// SWK_RUN_ZSLAB: does any voxel differ from the z = 0 voxel of its column?  (one streaming pass over mask and field map)
+__global__ void zinv_check_kernel(const uint8_t *mask, const float *field, size_t n, uint32_t nz, unsigned int *differs)
+{
+    bool d = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i - i % nz;
+        d |= (mask[i] != mask[c]) | (__float_as_uint(field[i]) != __float_as_uint(field[c]));
+    }
+    if (__any_sync(0xffffffffu, d) && (threadIdx.x & 31) == 0) atomicOr(differs, 1u);
+}
+// ... and the packed words (pack_voxels_kernel) of the z = 0 plane
+__global__ void pack_slab_kernel(const uint8_t *mask, const float *field, size_t nxy, uint32_t nz, uint32_t *out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nxy; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t b = __float_as_uint(field[i * nz]);
+        if ((b & 0x7f800000u) != 0x7f800000u) b += 8u;
+        out[i] = (b & 0xfffffff0u) | (uint32_t)mask[i * nz];
     }
 }
 
@@ -344,7 +367,7 @@ void swk_destroy(swk_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     for (DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox})
+                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab})
         release(*b);
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -382,6 +405,9 @@ int swk_set_phantom(swk_engine *e, const uint8_t *mask, const float *fieldmap_T,
     release(e->fieldmap);
     release(e->packed);
     e->packed_valid = false;
+    release(e->slab);
+    e->slab_valid = false;
+    e->z_invariant = -1;
     int rc;
     if ((rc = ensure(e, e->mask, V)) != SWK_OK) return rc;
     if (fieldmap_T && (rc = ensure(e, e->fieldmap, V * sizeof(float))) != SWK_OK) return rc;
@@ -638,7 +664,34 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     tr.mark("spin ordering");
     // compact voxel words for the FAST walk (built once per phantom)
     const bool want_packed = mode == SWK_MODE_FAST && e->fieldmap.p && e->mask_substrates <= 16 && !(flags & SWK_RUN_NO_PACK);
-    if (want_packed && !e->packed_valid) {
+    // opt-in: a phantom that does not depend on z is walked on its [nx][ny] slab (same words, table nz times smaller)
+    bool use_slab = false;
+    if (want_packed && ((flags & SWK_RUN_ZSLAB) || getenv("SWK_ZSLAB") != nullptr) && e->dims[2] > 1) {
+        const size_t V = (size_t)(e->dims[0] * e->dims[1] * e->dims[2]), nxy = (size_t)(e->dims[0] * e->dims[1]);
+        if (e->z_invariant < 0) {
+            unsigned int differs = 0;
+            unsigned int *flag = reinterpret_cast<unsigned int *>(static_cast<unsigned long long *>(e->counters.p) + 7); // zeroed above, unused by the walk
+            zinv_check_kernel<<<e->sm_count * 16, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), static_cast<const float *>(e->fieldmap.p), V,
+                                                                      (uint32_t)e->dims[2], flag);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&differs, flag, sizeof differs, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaStreamSynchronize(e->stream));
+            e->z_invariant = differs ? 0 : 1;
+            extra_launches++;
+        }
+        if (e->z_invariant == 1) {
+            if (!e->slab_valid) {
+                if ((rc = ensure(e, e->slab, nxy * sizeof(uint32_t))) != SWK_OK) return rc;
+                pack_slab_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), static_cast<const float *>(e->fieldmap.p), nxy,
+                                                                        (uint32_t)e->dims[2], static_cast<uint32_t *>(e->slab.p));
+                CK(cudaGetLastError());
+                e->slab_valid = true;
+                extra_launches++;
+            }
+            use_slab = true;
+        }
+    }
+    if (want_packed && !use_slab && !e->packed_valid) {
         const size_t V = (size_t)(e->dims[0] * e->dims[1] * e->dims[2]);
         if ((rc = ensure(e, e->packed, V * sizeof(uint32_t))) != SWK_OK) return rc;
         pack_voxels_kernel<<<e->sm_count * 16, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), static_cast<const float *>(e->fieldmap.p), V,
@@ -651,7 +704,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     WalkArgs A{};
     A.mask = static_cast<const uint8_t *>(e->mask.p);
     A.fieldmap = static_cast<const float *>(e->fieldmap.p);
-    A.packed = want_packed ? static_cast<const uint32_t *>(e->packed.p) : nullptr;
+    A.packed = want_packed ? static_cast<const uint32_t *>(use_slab ? e->slab.p : e->packed.p) : nullptr;
     A.nx = (uint32_t)e->dims[0]; A.ny = (uint32_t)e->dims[1]; A.nz = (uint32_t)e->dims[2];
     A.V = (int64_t)(e->dims[0] * e->dims[1] * e->dims[2]);
     for (int i = 0; i < 3; i++) A.fov[i] = e->fov[i];
@@ -701,7 +754,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     void (*kern)(const WalkArgs) = nullptr;
     if (mode == SWK_MODE_COMPAT) kern = stats_on ? walk_kernel<SWK_MODE_COMPAT, true> : walk_kernel<SWK_MODE_COMPAT, false>;
     else {
-        const int vox = A.packed ? VOX_PACKED : (A.fieldmap ? VOX_SPLIT : VOX_MASK);
+        const int vox = A.packed ? (use_slab ? VOX_SLAB : VOX_PACKED) : (A.fieldmap ? VOX_SPLIT : VOX_MASK);
         bool gruns = false; // does the timeline hold a run of gradient samples (swk_set_sequence: tl_run >= 2)?
         {
             const uint32_t *run = reinterpret_cast<const uint32_t *>(e->blob_h.data() + e->L.tl_run);
@@ -710,7 +763,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
 #define SWK_PICK2(V, G) (A.record ? (stats_on ? walk_fast_kernel<true, true, V, G> : walk_fast_kernel<false, true, V, G>) \
                                   : (stats_on ? walk_fast_kernel<true, false, V, G> : walk_fast_kernel<false, false, V, G>))
 #define SWK_PICK(V) (gruns ? SWK_PICK2(V, true) : SWK_PICK2(V, false))
-        kern = vox == VOX_PACKED ? SWK_PICK(VOX_PACKED) : (vox == VOX_SPLIT ? SWK_PICK(VOX_SPLIT) : SWK_PICK(VOX_MASK));
+        kern = vox == VOX_PACKED ? SWK_PICK(VOX_PACKED) : (vox == VOX_SLAB ? SWK_PICK(VOX_SLAB) : (vox == VOX_SPLIT ? SWK_PICK(VOX_SPLIT) : SWK_PICK(VOX_MASK)));
 #undef SWK_PICK
 #undef SWK_PICK2
     }
@@ -993,7 +1046,7 @@ uint64_t swk_device_bytes(const swk_engine *e)
     if (!e) return 0;
     uint64_t n = 0;
     for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox})
+                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab})
         n += b->bytes;
     return n;
 }
@@ -1149,6 +1202,9 @@ int swk_generate_phantom(swk_engine *e, const swk_phantom_spec *spec, swk_phanto
     release(e->fieldmap);
     release(e->packed);
     e->packed_valid = false;
+    release(e->slab);
+    e->slab_valid = false;
+    e->z_invariant = -1;
     if ((rc = ensure(e, e->mask, V)) != SWK_OK) return rc;
     if (calc && (rc = ensure(e, e->fieldmap, V * sizeof(float))) != SWK_OK) return rc;
     swk::phantom::FillResult fr;

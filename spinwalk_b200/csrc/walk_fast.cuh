@@ -152,7 +152,9 @@ __device__ __forceinline__ uint32_t ldg_voxel(const uint32_t *p)
 
 // VOX selects how a voxel is fetched: 0 = mask only (no fieldmap), 1 = mask byte + FP32 field (two gathers issued
 // together), 2 = one packed 32-bit word (field with its 4 low mantissa bits replaced by the substrate id).
-enum { VOX_MASK = 0, VOX_SPLIT = 1, VOX_PACKED = 2 };
+// 3 = the packed word of a phantom that is invariant along z (every cylinder phantom), fetched from its [nx][ny] slab: the same
+// words as variant 2 from a table nz times smaller (opt-in: SWK_RUN_ZSLAB, engine.cu run_impl).
+enum { VOX_MASK = 0, VOX_SPLIT = 1, VOX_PACKED = 2, VOX_SLAB = 3 };
 
 // GRUNS: the sequence holds runs of gradient samples (taken inside the inner loop); sequences without them get a kernel without that code.
 template <bool STATS, bool RECORD, int VOX, bool GRUNS>
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
     float field = 0.f;
     if (alive && VOX == VOX_SPLIT) field = __fmul_rn(__ldg(A.fieldmap + ind_cur), field_k);
     if (alive && VOX == VOX_PACKED) field = __fmul_rn(__uint_as_float(__ldg(A.packed + ind_cur) & 0xfffffff0u), field_k);
+    if (alive && VOX == VOX_SLAB) field = __fmul_rn(__uint_as_float(__ldg(A.packed + ((p0 >> fb) * ny + (p1 >> fb))) & 0xfffffff0u), field_k);
     float sg0 = sgt[3 * ts_old], sg1 = sgt[3 * ts_old + 1], sg2 = sgt[3 * ts_old + 2];
 
     uint32_t itr = 0;
@@ -343,8 +346,8 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
                     }
                     ind_new = (v0 * ny + v1) * nz + v2;
                     if (STATS) { chg = (ind_new != ind_cur) | fresh; st_mask += chg; }
-                    if (VOX == VOX_PACKED) { // one gather
-                        const uint32_t w = ldg_voxel(A.packed + ind_new);
+                    if (VOX == VOX_PACKED || VOX == VOX_SLAB) { // one gather
+                        const uint32_t w = ldg_voxel(A.packed + (VOX == VOX_SLAB ? v0 * ny + v1 : ind_new));
                         ts = w & 15u;
                         fv = __uint_as_float(w & 0xfffffff0u);
                     } else {                 // both gathers issued back to back

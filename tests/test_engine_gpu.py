@@ -331,3 +331,41 @@ def test_single_spin_and_ragged_sizes(sw, oracle):
             else:
                 for k in ("M1", "XYZ1", "T"):
                     assert np.array_equal(got[k], full[k][:, :n]), (mode, n, k)
+
+
+def test_zslab_walks_the_same_path(sw):
+    """SWK_RUN_ZSLAB (opt-in): a phantom whose mask and field map do not depend on z — every cylinder phantom — is walked on the packed
+    words of one z plane.  They are the words of the full table, so the results are the default FAST results bit for bit; a phantom
+    that does depend on z ignores the flag."""
+    case, mask, fm, fov, xyz0 = cases.se(n_spins=900)
+    assert (mask == mask[:, :, :1]).all() and (fm.view(np.uint32) == fm[:, :, :1].view(np.uint32)).all(), "the test phantom must be z-invariant"
+    cfg = cases.to_simconfig(case)
+    with sw.Engine(0) as e:
+        e.set_phantom(mask, fm, fov)
+        e.set_sequence(cfg)
+        e.set_spins(xyz0)
+        st0 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS)
+        base = e.download() + (e.sums(),)
+        st1 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_ZSLAB)
+        slab = e.download() + (e.sums(),)
+        st2 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_ZSLAB)
+    assert st1["n_launches"] == 3 and st2["n_launches"] == 1  # z-invariance check + slab packing happen once per phantom
+    for a, b in zip(base[:3], slab[:3]):
+        assert np.array_equal(a, b)
+    assert np.allclose(base[3], slab[3], rtol=1e-9, atol=1e-3)
+    for key in ("steps", "mask_gathers", "field_gathers", "rejects", "lost"):
+        assert st0[key] == st1[key], key
+    # not invariant along z: the flag changes nothing
+    case, mask, fm, fov, xyz0 = cases.multi_echo(n_spins=400)
+    cfg = cases.to_simconfig(case)
+    with sw.Engine(0) as e:
+        e.set_phantom(mask, fm, fov)
+        e.set_sequence(cfg)
+        e.set_spins(xyz0)
+        e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL)
+        base = e.download()
+        st = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_ZSLAB)
+        again = e.download()
+    assert st["n_launches"] == 2  # the check itself, then the normal table
+    for a, b in zip(base, again):
+        assert np.array_equal(a, b)
