@@ -27,7 +27,7 @@ void usage()
             "Usage: spinwalk [-g] [-l LOG] SUBCOMMAND ...\n"
             "  sim      -c,--configs FILE...   config. files as many as you want\n"
             "           -p,--use_cpu           not available: this engine has no CPU path\n"
-            "           -d,--device N[,M...]   select GPU device(s); [--compat] [--sums] [-q]\n"
+            "           -d,--device N[,M...]   select GPU device(s); [--compat] [--sums] [--zslab] [-q]\n"
             "  phantom  -c,--cylinder | -s,--sphere | -t,--two_pools | -p,--ply -i,--ply_file MESH.ply\n"
             "           -r,--radius [50]  -n,--orientation [90]  -v,--volume_fraction [4]  -f,--fov (required)  -z,--resolution (required)\n"
             "           -d,--dchi [0.11e-6]  -y,--oxy_level [0.75]  -e,--seed [-1]  -o,--output (required)  [--device N]\n"
@@ -234,6 +234,7 @@ int run_sim(Args &a)
         if (o == "-p" || o == "--use_cpu") use_cpu = true;
         else if (o == "--compat") opt.compat = true;
         else if (o == "--sums") opt.write_sums = true;
+        else if (o == "--zslab") setenv("SWK_ZSLAB", "1", 1); // opt-in z-slab voxel table (include/spinwalk_engine.h SWK_RUN_ZSLAB)
         else if (o == "-q") opt.quiet = true;
         else if (o == "-d" || o == "--device") {
             if (!a.one(v)) return fail_usage("--device: a number is required");
