@@ -18,7 +18,7 @@ const uint64_t kUndef = ~0ull;
 uint64_t rdn(const uint8_t *p, int n)
 {
     uint64_t v = 0;
-    for (int i = 0; i < n; i++) v |= (uint64_t)p[i] << (8 * i);
+    for (int i = 0; i < n && i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
     if (n < 8 && v == ((1ull << (8 * n)) - 1)) return kUndef; // undefined address of a narrower width
     return v;
 }
@@ -27,7 +27,7 @@ uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | p[1] << 8); }
 
 void put(std::vector<uint8_t> &b, uint64_t v, int n)
 {
-    for (int i = 0; i < n; i++) b.push_back((uint8_t)(v >> (8 * i)));
+    for (int i = 0; i < n; i++) b.push_back(i < 8 ? (uint8_t)(v >> (8 * i)) : (uint8_t)0); // n > 8: zero fill
 }
 void pad8(std::vector<uint8_t> &b)
 {
@@ -165,9 +165,11 @@ bool Reader::open(const std::string &path)
     if (!pread(sb, h, hn)) return false;
     const int ver = h[8];
     uint64_t root_oh = kUndef, btree = kUndef, heap = kUndef, base_field = 0;
+    auto sizes_ok = [&] { return (size_off_ == 2 || size_off_ == 4 || size_off_ == 8) && (size_len_ == 2 || size_len_ == 4 || size_len_ == 8); };
     if (ver == 0 || ver == 1) {
         size_off_ = h[13];
         size_len_ = h[14];
+        if (!sizes_ok()) return fail("unsupported size of offsets / lengths"); // they are strides into h[] below
         size_t p = (ver == 0) ? 24 : 28;
         base_field = rdn(h + p, size_off_);
         p += 4 * (size_t)size_off_; // base, free-space info, end of file, driver info
@@ -181,13 +183,12 @@ bool Reader::open(const std::string &path)
     } else if (ver == 2 || ver == 3) {
         size_off_ = h[9];
         size_len_ = h[10];
+        if (!sizes_ok()) return fail("unsupported size of offsets / lengths");
         base_field = rdn(h + 12, size_off_);
         root_oh = rdn(h + 12 + 3 * size_off_, size_off_);
     } else {
         return fail("superblock version " + std::to_string(ver) + " is not supported");
     }
-    if ((size_off_ != 2 && size_off_ != 4 && size_off_ != 8) || (size_len_ != 2 && size_len_ != 4 && size_len_ != 8))
-        return fail("unsupported size of offsets / lengths");
     base_ = (base_field && base_field != kUndef) ? base_field : sb; // addresses are relative to the base address (= user block size)
     if (root_oh == kUndef) return fail("root group has no object header");
     return load_root(base_ + root_oh, btree, heap);
