@@ -1,5 +1,5 @@
 """Kernel time of the C2 workload (all 50 FoV scales, reduced spin count) with the default packed table and with SWK_RUN_ZSLAB.
-Diagnostic, not the bench.  python scripts/zslab_probe.py [spins]"""
+Diagnostic, not the bench.  python scripts/zslab_probe.py [spins] [c2|c5|c1]"""
 import os
 import sys
 
@@ -8,7 +8,7 @@ import bench  # noqa: E402
 import spinwalk_b200 as sw  # noqa: E402
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
-cfg_kw, ph, _ = bench.workload("c2", S, None)
+cfg_kw, ph, _ = bench.workload(sys.argv[2] if len(sys.argv) > 2 else "c2", S, None)
 cfg = sw.SimConfig(**cfg_kw)
 eng = sw.Engine(0)
 eng.generate_phantom(bench.phantom_spec(ph))
