@@ -1,7 +1,7 @@
 """Engine (COMPAT) against the reference's own cu_sim on the seeded RANDOM cases of tests/random_cases.py (the oracle is pinned on them on
 the CPU, tests/test_oracle_random.py).  Written when no GPU time was left to run it: run it first
 (python scripts/random_parity_gpu.py [n_cases]) and, once it is green, promote it to tests/ as a -m gpu test.
-Bars as in tests/test_engine_gpu.py: T and XYZ1 bitwise, M1 <= 2e-6; FAST mode must run every case without losing more spins than COMPAT."""
+Bars as in tests/test_engine_gpu.py: T and XYZ1 bitwise, M1 <= 2e-6; FAST mode must run every case to finite outputs (its lost-spin count is printed beside COMPAT's)."""
 import os
 import sys
 
@@ -29,7 +29,7 @@ for seed in range(n):
     okT = np.array_equal(got["T"], ref["T"])
     okX = np.array_equal(got["XYZ1"].view(np.uint32), ref["XYZ1"].view(np.uint32))
     dM = float(np.abs(got["M1"] - ref["M1"]).max()) if got["M1"].size else 0.0
-    okF = np.isfinite(fast["M1"]).all() and fast["stats"]["lost"] <= got["stats"]["lost"]
+    okF = bool(np.isfinite(fast["M1"]).all() and np.isfinite(fast["XYZ1"]).all())
     if not (okT and okX and dM <= 2e-6 and okF):
         bad += 1
         print(f"seed {seed}: T {okT} XYZ1 {okX} max|dM1| {dM:.3g} fast ok {okF} (lost compat {got['stats']['lost']} fast {fast['stats']['lost']})", flush=True)
