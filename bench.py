@@ -186,12 +186,28 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def oracle_case(cfg_kw, n, fov, n_spins=None, scales=None):
+    """SimConfig keyword arguments of a workload -> oracle.pyoracle.Case (times in timepoints, config_reader.cpp:39-46) for the
+    reference legs (CPU reference, reference cu_sim) and the parity tests."""
+    from oracle import pyoracle as po
+
+    dt = cfg_kw["timestep_us"]
+    tp = lambda us: [int(t) // dt for t in us]  # noqa: E731
+    return po.Case(fov=tuple(fov), phantom_size=(n, n, n), n_spins=n_spins or cfg_kw["n_spins"], TR_us=cfg_kw["TR_us"], timestep_us=dt,
+                   seed=cfg_kw["seed"], B0=cfg_kw["B0"], TE_tp=tp(cfg_kw["TE_us"]), RF_FA_deg=cfg_kw["RF_FA_deg"], RF_PH_deg=cfg_kw["RF_PH_deg"],
+                   RF_tp=tp(cfg_kw["RF_T_us"]), n_dummy_scan=cfg_kw.get("n_dummy_scan", 0), linear_phase_cycling=cfg_kw.get("linear_phase_cycling", 0.0),
+                   gradient_tp=tp(cfg_kw.get("gradient_T_us", [])), gradX_mTm=cfg_kw.get("gradient_X_mTm", []), gradY_mTm=cfg_kw.get("gradient_Y_mTm", []),
+                   gradZ_mTm=cfg_kw.get("gradient_Z_mTm", []), diffusivity=cfg_kw["diffusivity"], T1_ms=cfg_kw["T1_ms"], T2_ms=cfg_kw["T2_ms"], pXY=cfg_kw["pXY"],
+                   scales=list(cfg_kw["scales"] if scales is None else scales), scale_type=cfg_kw["scale_type"], cross_fov=cfg_kw["cross_fov"],
+                   max_iterations=cfg_kw["max_iterations"])
+
+
 def cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0, threads=None):
     """The reference's own CPU implementation of the path (oracle/_ref/libswref_cpu.so = unmodified kernels.cu built
     by g++, std::mt19937 arithmetic; falls back to the C port) on a bounded sample of the same workload."""
     from oracle import pyoracle as po
 
-    n, nz = ph["n"], ph["n"]
+    n = ph["n"]
     mask, fm = full_phantom(ph, mask2, fm2)
     threads = threads or os.cpu_count() or 1
     kind = "reference" if po.have_ref_cpu() else "port"
@@ -199,14 +215,7 @@ def cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0, threads=None):
         po.build(ref=False)
 
     def run(n_spins, scales):
-        c = po.Case(fov=tuple(fov), phantom_size=(n, n, nz), n_spins=n_spins, TR_us=cfg_kw["TR_us"], timestep_us=cfg_kw["timestep_us"],
-                    seed=cfg_kw["seed"], B0=cfg_kw["B0"], TE_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["TE_us"]],
-                    RF_FA_deg=cfg_kw["RF_FA_deg"], RF_PH_deg=cfg_kw["RF_PH_deg"], RF_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["RF_T_us"]],
-                    n_dummy_scan=cfg_kw.get("n_dummy_scan", 0), linear_phase_cycling=cfg_kw.get("linear_phase_cycling", 0.0),
-                    gradient_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw.get("gradient_T_us", [])],
-                    gradX_mTm=cfg_kw.get("gradient_X_mTm", []), gradY_mTm=cfg_kw.get("gradient_Y_mTm", []), gradZ_mTm=cfg_kw.get("gradient_Z_mTm", []),
-                    diffusivity=cfg_kw["diffusivity"], T1_ms=cfg_kw["T1_ms"], T2_ms=cfg_kw["T2_ms"], pXY=cfg_kw["pXY"],
-                    scales=scales, scale_type=cfg_kw["scale_type"], cross_fov=cfg_kw["cross_fov"], max_iterations=cfg_kw["max_iterations"])
+        c = oracle_case(cfg_kw, n, fov, n_spins, scales)
         x0 = make_positions(n_spins, fov, cfg_kw["seed"])
         f = po.run_ref if kind == "reference" else po.run_oracle
         r = f(c, fm, mask, x0, flavour=po.RNG_MT19937, threads=threads)
@@ -238,14 +247,7 @@ def reference_cuda(cfg_kw, ph, mask2, fm2, fov, device, target_s=10.0):
     mask, fm = full_phantom(ph, mask2, fm2)
 
     def run(n_spins):
-        c = po.Case(fov=tuple(fov), phantom_size=(n, n, n), n_spins=n_spins, TR_us=cfg_kw["TR_us"], timestep_us=cfg_kw["timestep_us"],
-                    seed=cfg_kw["seed"], B0=cfg_kw["B0"], TE_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["TE_us"]],
-                    RF_FA_deg=cfg_kw["RF_FA_deg"], RF_PH_deg=cfg_kw["RF_PH_deg"], RF_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw["RF_T_us"]],
-                    n_dummy_scan=cfg_kw.get("n_dummy_scan", 0), linear_phase_cycling=cfg_kw.get("linear_phase_cycling", 0.0),
-                    gradient_tp=[t // cfg_kw["timestep_us"] for t in cfg_kw.get("gradient_T_us", [])],
-                    gradX_mTm=cfg_kw.get("gradient_X_mTm", []), gradY_mTm=cfg_kw.get("gradient_Y_mTm", []), gradZ_mTm=cfg_kw.get("gradient_Z_mTm", []),
-                    diffusivity=cfg_kw["diffusivity"], T1_ms=cfg_kw["T1_ms"], T2_ms=cfg_kw["T2_ms"], pXY=cfg_kw["pXY"],
-                    scales=cfg_kw["scales"], scale_type=cfg_kw["scale_type"], cross_fov=cfg_kw["cross_fov"], max_iterations=cfg_kw["max_iterations"])
+        c = oracle_case(cfg_kw, n, fov, n_spins)
         r = po.run_ref_cuda(c, fm, mask, make_positions(n_spins, fov, cfg_kw["seed"]), device=device)
         return c.total_steps(), r["kernel_ms"] * 1e-3
 

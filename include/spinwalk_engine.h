@@ -47,9 +47,13 @@ enum swk_scale_type { SWK_SCALE_FOV = 0, SWK_SCALE_GRADIENT = 1, SWK_SCALE_PHASE
  *   SWK_MODE_COMPAT  the reference CUDA build's arithmetic: thrust::minstd_rand seeded seed+spin and
  *                    discarded seed+spin (kernels.cu:77-88), normal = -sqrt(2) erfcinvf(2p), FP64 positions
  *                    in metres.  Bit-exact walks against the reference's own cu_sim on the same device.
- *   SWK_MODE_FAST    Philox4x32-10 counter RNG keyed by (seed, global spin id, scale index), Box-Muller
- *                    normals, positions as (voxel, fraction) in grid units in FP32.  Same stochastic
- *                    process; agrees with the reference within Monte-Carlo error. */
+ *   SWK_MODE_FAST    Philox4x32-10 counter RNG (fixed key; counter = Philox block index, seed, global spin id, stream tag):
+ *                    round r of a spin draws its three normals from block r >> 1 (Box-Muller on 23-bit uniforms), and every
+ *                    scale replays the same stream, like the reference re-seeding seed+spin per scale (kernels.cu:77-88); the
+ *                    permeability uniform is a separate Philox2x32-10 stream keyed by a fold of the seed, counter = (round, spin id).
+ *                    Positions are 32-bit fixed-point grid coordinates.  Same stochastic process; agrees with the reference
+ *                    within Monte-Carlo error (tests/test_fast_parity_gpu.py).  Deviations from the reference's arithmetic:
+ *                    DESIGN.md §2. */
 enum swk_mode { SWK_MODE_COMPAT = 0, SWK_MODE_FAST = 1 };
 
 /* ≙ struct parameters AFTER parameters::prepare (simulation_parameters.cuh:176-201,227-245).
@@ -140,16 +144,21 @@ int swk_set_spins(swk_engine *e, const float *XYZ0, const float *M0, uint32_t sp
 /* ---- run all scales with inputs resident on the device (≙ the scale loop, monte_carlo.cu:273-337) ----
  * scales: host float [n_scales].  flags: SWK_OUT_*.  d_sums: DEVICE pointer to double
  * [n_scales][n_TE][n_substrate][4] = {sum Mx, sum My, sum Mz, count} per tissue at each echo, or NULL
- * (engine-owned buffer is used; read it with swk_get_sums).  The buffer is zeroed by the run. */
+ * (engine-owned buffer is used; read it with swk_get_sums).  The buffer is overwritten by the run.  The sums are accumulated in
+ * integer fixed point (2^-22 per component and spin): they are bit-reproducible run to run and independent of how the spins are
+ * sharded, sliced or ordered. */
 enum { SWK_OUT_M1 = 1, SWK_OUT_XYZ1 = 2, SWK_OUT_T = 4, SWK_OUT_ALL = 7,
        SWK_RUN_STATS = 16,  /* count gathers / rejections (swk_stats); slightly slower kernel variant */
        SWK_RUN_NO_SORT = 32, /* simulate spins in caller order (no substrate/Morton locality order); for A/B tests */
        SWK_RUN_NO_PACK = 64, /* FAST mode: gather mask byte + FP32 field separately instead of the packed voxel word */
        SWK_RUN_NO_REBIN = 128, /* FAST mode: never pause a long run (many TRs) to re-sort the spins by their current voxel; for A/B tests */
-       SWK_RUN_ZSLAB = 256 /* FAST mode, opt-in (also: environment SWK_ZSLAB=1): when mask and field map do not depend on z (checked on the device;
-                              every cylinder phantom of `spinwalk phantom -c`), fetch the packed voxel words from the [nx][ny] slab instead of
-                              the [nx][ny][nz] table — the same words, hence the same results bit for bit, from an L1/L2-resident table.
-                              Ignored (normal table) for any other phantom. */ };
+       SWK_RUN_ZSLAB = 256, /* accepted and ignored (round 1's opt-in; the z-slab table is the default now, see SWK_RUN_NO_ZSLAB) */
+       SWK_RUN_NO_ZSLAB = 512, /* FAST mode: by default a phantom whose mask and field map do not depend on z (checked once per phantom on the
+                              device; every cylinder phantom of `spinwalk phantom -c`) is walked on the packed voxel words of ONE z plane — the
+                              same words, hence the same results bit for bit, from an L1/L2-resident [nx][ny] table instead of [nx][ny][nz].
+                              This flag (or environment SWK_NO_ZSLAB=1) keeps the full table: A/B tests, the gather-roofline measurement. */
+       SWK_RUN_NO_SHARE = 1024 /* FAST mode: every thread generates its own normals (the PRIVATE kernel variant) even when several scales could
+                              share one generation per spin (walk_fast.cuh); same results bit for bit; for A/B tests (also: SWK_NO_SHARE=1) */ };
 int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags,
                    double *d_sums);
 

@@ -18,6 +18,7 @@ ap.add_argument("--modes", type=str, default="fast,compat")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--flags", type=int, default=sw.OUT_ALL)
 ap.add_argument("--nosort", action="store_true")
+ap.add_argument("--dup", type=int, default=1, help="run every scale DUP times in one launch (DUP >= 2: the SHARED kernel variant, DUP walkers share a spin's normals)")
 ap.add_argument("--nopack", action="store_true")
 args = ap.parse_args()
 if args.nosort:
@@ -40,10 +41,10 @@ eng.set_spins(bench.make_positions(args.spins, fov, 10))
 for mode_name in args.modes.split(","):
     mode = sw.MODE_FAST if mode_name == "fast" else sw.MODE_COMPAT
     for s in [float(x) for x in args.scales.split(",")]:
-        st = eng.run_device(scales=[s], mode=mode, flags=args.flags | sw.RUN_STATS)
+        st = eng.run_device(scales=[s] * args.dup, mode=mode, flags=args.flags | sw.RUN_STATS)
         best = 1e30
         for _ in range(args.reps):
-            best = min(best, eng.run_device(scales=[s], mode=mode, flags=args.flags)["kernel_ms"])
-        steps = args.spins * 800
+            best = min(best, eng.run_device(scales=[s] * args.dup, mode=mode, flags=args.flags)["kernel_ms"])
+        steps = args.spins * 800 * args.dup
         print(f"{mode_name:6s} scale {s:8.4f}: {steps / best / 1e6:8.2f} Gsteps/s  kernel {best:8.2f} ms  p_chg {st['mask_gathers'] / st['steps']:.3f} "
               f"rej/step {st['rejects'] / st['steps']:.4f} lost {st['lost']}", flush=True)

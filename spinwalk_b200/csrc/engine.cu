@@ -85,8 +85,12 @@ struct swk_engine {
     uint32_t spin_first = 0, n_local = 0;
     bool has_m0 = false, has_spins = false;
 
+    size_t mem_pitch = 0x7fffffff; // cudaDeviceProp::memPitch: the largest pitch cudaMemcpy2D accepts (SWK_MEMPITCH overrides, tests)
     // run state / outputs
     DevBuf scales, M1, XYZ1, T, sums, counters;
+    DevBuf stage;     // staging rows of the per-spin results (walk_kernel.cuh WalkArgs::stage)
+    DevBuf sums_fx;   // fixed-point ensemble sums the kernels accumulate; converted into `sums` after the walk
+    DevBuf scale_tab; // per-scale constants of the FAST kernel
     uint32_t n_scales = 0, n_te = 0, last_slices = 1;
     uint64_t host_rows = 0, host_row_first = 0; // swk_set_host_rows: host arrays are [K][host_rows][...], ours start at row host_row_first
     uint64_t trj = 1;
@@ -169,18 +173,26 @@ __device__ __forceinline__ uint64_t spread3(uint32_t v)
     x = (x | (x << 2)) & 0x9249249249249249ull;
     return x;
 }
-// Compact voxel word of SWK_MODE_FAST: the FP32 field (Tesla) rounded to 20 mantissa bits, substrate id in the 4 low bits.
-// One 4-byte gather per voxel change instead of a byte + a float from two arrays; relative field error <= 2^-21.
+// Compact voxel word of SWK_MODE_FAST: the FP32 field (Tesla) moved to the NEAREST value whose 4 low mantissa bits spell the substrate
+// id (|error| <= 8 ulp = 2^-20 relative).  One 4-byte gather per voxel change instead of a byte + a float from two arrays, and the word
+// is used AS the field value (no masking in the walk).
+__device__ __forceinline__ uint32_t pack_word(float field, uint32_t ts)
+{
+    const uint32_t b = __float_as_uint(field), sign = b & 0x80000000u;
+    uint32_t mag = b & 0x7fffffffu;
+    if ((mag & 0x7f800000u) == 0x7f800000u) return sign | (mag & ~15u) | ts; // inf / nan: keep the class
+    const int d = (int)(mag & 15u) - (int)ts;
+    mag = (mag & ~15u) | ts;
+    if (d > 8) mag += 16u;                    // (a carry into the exponent is still the right value)
+    else if (d < -8 && mag >= 16u) mag -= 16u;
+    return sign | mag;
+}
 __global__ void pack_voxels_kernel(const uint8_t *mask, const float *field, size_t n, uint32_t *out)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        uint32_t b = __float_as_uint(field[i]);
-        if ((b & 0x7f800000u) != 0x7f800000u) b += 8u; // round to nearest (carry into the exponent is still the right value)
-        out[i] = (b & 0xfffffff0u) | (uint32_t)mask[i];
-    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = pack_word(field[i], mask[i]);
 }
 
-// SWK_RUN_ZSLAB: does any voxel differ from the z = 0 voxel of its column?  (one streaming pass over mask and field map)
+// z-slab table: does any voxel differ from the z = 0 voxel of its column?  (one streaming pass over mask and field map)
 __global__ void zinv_check_kernel(const uint8_t *mask, const float *field, size_t n, uint32_t nz, unsigned int *differs)
 {
     bool d = false;
@@ -193,11 +205,7 @@ __global__ void zinv_check_kernel(const uint8_t *mask, const float *field, size_
 // ... and the packed words (pack_voxels_kernel) of the z = 0 plane
 __global__ void pack_slab_kernel(const uint8_t *mask, const float *field, size_t nxy, uint32_t nz, uint32_t *out)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nxy; i += (size_t)gridDim.x * blockDim.x) {
-        uint32_t b = __float_as_uint(field[i * nz]);
-        if ((b & 0x7f800000u) != 0x7f800000u) b += 8u;
-        out[i] = (b & 0xfffffff0u) | (uint32_t)mask[i * nz];
-    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nxy; i += (size_t)gridDim.x * blockDim.x) out[i] = pack_word(field[i * nz], mask[i * nz]);
 }
 
 // With slice_len != 0 the slice number of the spin (id / slice_len) leads the key, so that the sorted order is slice-major
@@ -245,6 +253,39 @@ __global__ void rebin_keys_kernel(const uint32_t *state_vox, const uint4 *state_
     const uint32_t vz = v % nz, vy = (v / nz) % ny, vx = v / (nz * ny);
     keys[i] = ((uint64_t)(i / n_local) << 56) | ((uint64_t)(255u - ts) << 48) | (spread3(vx) << 2) | (spread3(vy) << 1) | spread3(vz);
     ids[i] = (uint32_t)(i % n_local);
+}
+
+// Staging rows -> the reference's output layouts (monte_carlo.cu:61-70), rows [r0, r1) of every scale: a streaming pass, one 16-byte
+// slot per thread, consecutive threads write consecutive elements of M1 / T / XYZ1.
+__global__ void unpack_rows_kernel(const uint4 *stage, uint32_t row_slots, uint32_t n_te, size_t S, size_t r0, size_t r1, uint32_t K, float *M1, uint8_t *T,
+                                   float *XYZ1)
+{
+    const size_t per_scale = (r1 - r0) * row_slots, total = per_scale * K;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t k = i / per_scale, rem = i - k * per_scale;
+        const size_t row = k * S + r0 + rem / row_slots;
+        const uint32_t e = (uint32_t)(rem % row_slots);
+        const uint4 v = __ldcs(stage + row * row_slots + e);
+        if (e < n_te) {
+            if (M1) {
+                float *d = M1 + (row * n_te + e) * 3;
+                __stcs(d + 0, __uint_as_float(v.x)); __stcs(d + 1, __uint_as_float(v.y)); __stcs(d + 2, __uint_as_float(v.z));
+            }
+            if (T) T[row * n_te + e] = (uint8_t)v.w;
+        } else if (XYZ1) {
+            float *d = XYZ1 + row * 3;
+            __stcs(d + 0, __uint_as_float(v.x)); __stcs(d + 1, __uint_as_float(v.y)); __stcs(d + 2, __uint_as_float(v.z));
+        }
+    }
+}
+
+// fixed-point ensemble sums (walk_kernel.cuh echo_sums_add) -> double [K][E][n_sub][4]
+__global__ void sums_to_double_kernel(const unsigned long long *fx, size_t n, double *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long v = (long long)fx[i];
+    out[i] = (i & 3u) == 3u ? (double)v : (double)v * (1.0 / (double)kSumScale);
 }
 
 // key of the permeability stream (walk_fast.cuh philox2x32_10): a 32-bit fold of the run's seed
@@ -358,6 +399,8 @@ int swk_create(int device_id, swk_engine **out)
     }
     e->sm_count = prop.multiProcessorCount;
     e->smem_optin = prop.sharedMemPerBlockOptin;
+    e->mem_pitch = prop.memPitch;
+    if (const char *ev = getenv("SWK_MEMPITCH")) e->mem_pitch = (size_t)strtoull(ev, nullptr, 10); // test hook: exercise the per-scale copies
     *out = e;
     return SWK_OK;
 }
@@ -367,7 +410,7 @@ void swk_destroy(swk_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     for (DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab})
+                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab})
         release(*b);
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -563,12 +606,99 @@ int swk_set_spins(swk_engine *e, const float *XYZ0, const float *M0, uint32_t sp
     return SWK_OK;
 }
 
+} // extern "C"
+
 // Host destinations of a pipelined run (swk_run): results of slice i are copied back while slice i+1 computes.
 struct HostOut {
     float *M1 = nullptr;
     float *XYZ1 = nullptr;
     uint8_t *T = nullptr;
 };
+
+// Rows [.., +width) of K scale blocks, device -> host.  cudaMemcpy2DAsync rejects pitches above cudaDeviceProp::memPitch (2^31 - 1):
+// a per-scale block of M1 or XYZ1 of 2 GiB or more (1e8 spins x 2 echoes; trajectories) would fail with "invalid pitch" after the whole
+// simulation has run.  One plain copy when the blocks are contiguous on both sides, one 2-D copy when the pitches fit, else one plain
+// copy per scale.
+static cudaError_t copy_rows(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, size_t K, size_t pitch_limit, cudaStream_t st)
+{
+    if (width == 0 || K == 0) return cudaSuccess;
+    if (K == 1 || (dpitch == width && spitch == width)) return cudaMemcpyAsync(dst, src, width * K, cudaMemcpyDeviceToHost, st);
+    if (dpitch <= pitch_limit && spitch <= pitch_limit) return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, K, cudaMemcpyDeviceToHost, st);
+    for (size_t k = 0; k < K; k++) {
+        const cudaError_t ce = cudaMemcpyAsync(dst + k * dpitch, src + k * spitch, width, cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) return ce;
+    }
+    return cudaSuccess;
+}
+
+// Per-scale constants of the FAST kernel (walk_fast.cuh ScaleConst): fraction bits of the fixed-point position, step sigma per
+// (substrate, axis) in fixed-point units, unit conversions.  Double precision, once per run.
+static void scale_constants(const swk_engine *e, const float *scales, uint32_t K, int scale_type, std::vector<uint8_t> &tab, uint32_t &stride)
+{
+    const uint32_t ns = e->P.n_substrate;
+    const uint32_t sgt_off = (uint32_t)((sizeof(ScaleConst) + 15) / 16 * 16);
+    stride = (uint32_t)((sgt_off + 3 * ns * sizeof(float) + 15) / 16 * 16);
+    tab.assign((size_t)stride * K, 0);
+    const double *tsig = reinterpret_cast<const double *>(e->blob_h.data() + e->L.sigma);
+    const uint32_t n3[3] = {(uint32_t)e->dims[0], (uint32_t)e->dims[1], (uint32_t)e->dims[2]};
+    double inv_h[3]; // grid units per metre at scale 1
+    for (int i = 0; i < 3; i++) inv_h[i] = (double)n3[i] / (double)e->fov[i];
+    for (uint32_t k = 0; k < K; k++) {
+        ScaleConst sc{};
+        sc.fscale = 1.f; sc.gscale = 1.f; sc.lin_pc = e->P.linear_phase_cycling;
+        if (scale_type == SWK_SCALE_FOV) sc.fscale = scales[k];
+        else if (scale_type == SWK_SCALE_GRADIENT) sc.gscale = scales[k];
+        else sc.lin_pc = e->P.linear_phase_cycling * scales[k]; // monte_carlo.cu:303 (one FP32 product)
+        double smax = 0.;
+        for (uint32_t s = 0; s < ns; s++)
+            for (int i = 0; i < 3; i++) smax = std::max(smax, tsig[s] * inv_h[i] / (double)sc.fscale);
+        const uint32_t nmax = std::max(n3[0], std::max(n3[1], n3[2]));
+        int f = 22;
+        while (f > 0 && ((double)(nmax + 1u) * (double)(1u << f) + 4194304. > 4294967296.)) f--; // (b) of walk_fast.cuh
+        while (f > 0 && 5.7 * smax * (double)(1u << f) >= 4194304.) f--;                           // (a)
+        sc.fb = (uint32_t)f;
+        sc.sgt_off = sgt_off;
+        const double two_f = (double)(1u << f);
+        for (int i = 0; i < 3; i++) {
+            sc.unit_m[i] = (double)sc.fscale / (inv_h[i] * two_f);
+            sc.pos_k[i] = inv_h[i] * two_f;
+            sc.pos_hi[i] = (double)n3[i] * two_f - 1.;
+            sc.umk[i] = (float)((double)sc.fscale / (inv_h[i] * two_f) * 1e-3 * (double)e->P.timestep_us * 1e-6 * kGamma * kRad2Deg); // kernels.cu:185
+        }
+        uint8_t *rec = tab.data() + (size_t)k * stride;
+        memcpy(rec, &sc, sizeof sc);
+        float *sgt = reinterpret_cast<float *>(rec + sgt_off);
+        for (uint32_t s = 0; s < ns; s++)
+            for (int i = 0; i < 3; i++) sgt[3 * s + i] = (float)(tsig[s] * inv_h[i] / (double)sc.fscale * two_f);
+    }
+}
+
+// scales per block of the SHARED FAST kernel: the group size in [5, 16] that wastes the fewest warp slots in the last group, larger
+// groups first (more walkers share one generation of normals); runs with fewer than 5 scales take them all in one group.
+static uint32_t shared_group(uint32_t K)
+{
+    const uint32_t gmax = SWK_FAST_SHARED_MAXT / 32;
+    if (K <= gmax) return K;
+    uint32_t best = gmax, best_waste = 0xffffffffu;
+    for (uint32_t g = gmax; g >= 5; g--) {
+        const uint32_t waste = (K + g - 1) / g * g - K;
+        if (waste < best_waste) { best = g; best_waste = waste; }
+    }
+    return best;
+}
+
+typedef void (*walk_fn)(const WalkArgs);
+
+template <bool SHARED>
+static walk_fn pick_fast(int vox, bool gruns, bool record, bool stats)
+{
+#define SWK_PICK2(V, G) (record ? (stats ? walk_fast_kernel<true, true, V, G, SHARED> : walk_fast_kernel<false, true, V, G, SHARED>) \
+                                : (stats ? walk_fast_kernel<true, false, V, G, SHARED> : walk_fast_kernel<false, false, V, G, SHARED>))
+#define SWK_PICK(V) (gruns ? SWK_PICK2(V, true) : SWK_PICK2(V, false))
+    return vox == VOX_PACKED ? SWK_PICK(VOX_PACKED) : (vox == VOX_SLAB ? SWK_PICK(VOX_SLAB) : (vox == VOX_SPLIT ? SWK_PICK(VOX_SPLIT) : SWK_PICK(VOX_MASK)));
+#undef SWK_PICK
+#undef SWK_PICK2
+}
 
 static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags, double *d_sums,
                     uint32_t n_slices, const HostOut *host)
@@ -593,17 +723,24 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     CK(cudaSetDevice(e->device));
 
     const size_t K = n_scales, S = e->n_local, E = e->n_te, ns = e->P.n_substrate;
+    const bool record = e->P.record_trajectory != 0;
+    // staging rows carry M1, T and the final position; recorded trajectories are written straight into XYZ1
+    const bool want_stage = (flags & (SWK_OUT_M1 | SWK_OUT_T)) || ((flags & SWK_OUT_XYZ1) && !record);
+    const size_t stage_row = E + 1;
     int rc;
     if ((rc = ensure(e, e->scales, K * sizeof(float))) != SWK_OK) return rc;
     if ((rc = ensure(e, e->M1, (flags & SWK_OUT_M1) ? K * S * E * 3 * sizeof(float) : 0)) != SWK_OK) return rc;
     if ((rc = ensure(e, e->XYZ1, (flags & SWK_OUT_XYZ1) ? K * S * e->trj * 3 * sizeof(float) : 0)) != SWK_OK) return rc;
     if ((rc = ensure(e, e->T, (flags & SWK_OUT_T) ? K * S * E : 0)) != SWK_OK) return rc;
+    if ((rc = ensure(e, e->stage, want_stage ? K * S * stage_row * sizeof(uint4) : 0)) != SWK_OK) return rc;
     if ((rc = ensure(e, e->sums, std::max<size_t>(K * E * ns * 4, 1) * sizeof(double))) != SWK_OK) return rc;
+    if ((rc = ensure(e, e->sums_fx, std::max<size_t>(K * E * ns * 4, 1) * sizeof(unsigned long long))) != SWK_OK) return rc;
     if ((rc = ensure(e, e->counters, 8 * sizeof(unsigned long long))) != SWK_OK) return rc;
     double *sums = d_sums ? d_sums : static_cast<double *>(e->sums.p);
 
     // ---- slices: contiguous id ranges launched one after the other (1 = the whole shard in one launch) ----
     if (n_slices < 1) n_slices = 1;
+    n_slices = std::min<uint32_t>(n_slices, 256u); // the slice number is the top byte of the sort key
     uint32_t slice_len = (uint32_t)S;
     if (n_slices > 1) {
         slice_len = (uint32_t)(((S + n_slices - 1) / n_slices + kBlock - 1) / kBlock * kBlock);
@@ -623,11 +760,10 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     Trace tr;
     CK(cudaMemcpyAsync(e->scales.p, scales, K * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(cudaEventRecord(e->evA, e->stream));
-    // outputs start at zero: lost spins / unwritten echoes read back as 0 (monte_carlo.cu:256,259-260)
-    if (e->M1.p) CK(cudaMemsetAsync(e->M1.p, 0, e->M1.bytes, e->stream));
-    if (e->XYZ1.p) CK(cudaMemsetAsync(e->XYZ1.p, 0, e->XYZ1.bytes, e->stream));
-    if (e->T.p) CK(cudaMemsetAsync(e->T.p, 0, e->T.bytes, e->stream));
-    if (E * ns) CK(cudaMemsetAsync(sums, 0, K * E * ns * 4 * sizeof(double), e->stream));
+    // Every element of M1 / T / XYZ1 is written by the unpack pass (abandoned spins and echoes that never fire are staged as zeros, like the
+    // reference's zero-initialised outputs, monte_carlo.cu:256,259-260); only recorded trajectories, which walkers write slot by slot, start at zero.
+    if (e->XYZ1.p && record) CK(cudaMemsetAsync(e->XYZ1.p, 0, e->XYZ1.bytes, e->stream));
+    if (E * ns) CK(cudaMemsetAsync(e->sums_fx.p, 0, K * E * ns * 4 * sizeof(unsigned long long), e->stream));
     CK(cudaMemsetAsync(e->counters.p, 0, e->counters.bytes, e->stream));
 
     tr.mark("alloc + memset enqueue");
@@ -664,9 +800,10 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     tr.mark("spin ordering");
     // compact voxel words for the FAST walk (built once per phantom)
     const bool want_packed = mode == SWK_MODE_FAST && e->fieldmap.p && e->mask_substrates <= 16 && !(flags & SWK_RUN_NO_PACK);
-    // opt-in: a phantom that does not depend on z is walked on its [nx][ny] slab (same words, table nz times smaller)
+    // a phantom that does not depend on z (every cylinder phantom of `spinwalk phantom -c`) is walked on its [nx][ny] slab: the same
+    // words, hence the same results bit for bit, from a table nz times smaller (L1/L2 resident).  Checked once per phantom on the device.
     bool use_slab = false;
-    if (want_packed && ((flags & SWK_RUN_ZSLAB) || getenv("SWK_ZSLAB") != nullptr) && e->dims[2] > 1) {
+    if (want_packed && !(flags & SWK_RUN_NO_ZSLAB) && getenv("SWK_NO_ZSLAB") == nullptr && e->dims[2] > 1) {
         const size_t V = (size_t)(e->dims[0] * e->dims[1] * e->dims[2]), nxy = (size_t)(e->dims[0] * e->dims[1]);
         if (e->z_invariant < 0) {
             unsigned int differs = 0;
@@ -733,55 +870,104 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     A.order = e->order_valid ? static_cast<const uint32_t *>(e->order.p) : nullptr;
     A.spin_first = e->spin_first;
     A.n_local = e->n_local;
-    A.M1 = static_cast<float *>(e->M1.p);
-    A.XYZ1 = static_cast<float *>(e->XYZ1.p);
-    A.T = static_cast<uint8_t *>(e->T.p);
-    A.sums = (E * ns) ? sums : nullptr;
+    A.stage = static_cast<uint4 *>(e->stage.p);
+    A.stage_row = (uint32_t)stage_row;
+    A.XYZ1 = record ? static_cast<float *>(e->XYZ1.p) : nullptr;
+    A.sums_fx = (E * ns) ? static_cast<unsigned long long *>(e->sums_fx.p) : nullptr;
     A.counters = static_cast<unsigned long long *>(e->counters.p);
     A.trj = e->trj;
+    {
+        const float *pxy = reinterpret_cast<const float *>(e->blob_h.data() + e->L.pXY);
+        for (size_t i = 0; i < ns * ns; i++) A.perm_draws |= (pxy[i] > 0.f && pxy[i] < 1.f) ? 1 : 0;
+    }
 
-    // shared memory: sequence tables (when they fit) + block sums
-    const size_t bsum_bytes = A.sums ? E * ns * 4 * sizeof(float) : 0;
+    const bool stats_on = (flags & SWK_RUN_STATS) != 0;
     const size_t smem_cap = std::min<size_t>(e->smem_optin, 96 * 1024);
-    if (bsum_bytes > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
-    A.blob_in_smem = (e->L.bytes + bsum_bytes + (3 * ns + 3) * sizeof(float) <= smem_cap) ? 1 : 0;
-    const size_t sgt_bytes = (mode == SWK_MODE_FAST) ? (3 * ns + 3) * sizeof(float) : 0;
-    const size_t smem = (A.blob_in_smem ? e->L.bytes : 0) + bsum_bytes + sgt_bytes;
     if (mode == SWK_MODE_FAST && (uint64_t)A.V >= (1ull << 32)) return fail(e, SWK_ERR_INVALID, "SWK_MODE_FAST indexes voxels with 32 bits: phantom too large");
     if (mode == SWK_MODE_FAST && std::max(A.nx, std::max(A.ny, A.nz)) > (1u << 20)) return fail(e, SWK_ERR_INVALID, "SWK_MODE_FAST: more than 2^20 voxels along one axis");
 
-    const bool stats_on = (flags & SWK_RUN_STATS) != 0;
-    void (*kern)(const WalkArgs) = nullptr;
-    if (mode == SWK_MODE_COMPAT) kern = stats_on ? walk_kernel<SWK_MODE_COMPAT, true> : walk_kernel<SWK_MODE_COMPAT, false>;
-    else {
+    // ---- kernel variants and their shared memory ----
+    // COMPAT: [tables] [block sums].  FAST: [tables] [block sums x scales of the block] [scale constants] [normals, SHARED variant].
+    walk_fn kern = nullptr, kern_private = nullptr; // FAST: `kern` is the variant of a launch that starts at scan 0, `kern_private` the one of resumed legs
+    size_t smem = 0, smem_private = 0;
+    unsigned block = kBlock;
+    const size_t bsum_bytes = A.sums_fx ? E * ns * 4 * sizeof(long long) : 0;
+    bool shared_variant = false;
+    if (mode == SWK_MODE_COMPAT) {
+        if (bsum_bytes > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
+        A.blob_in_smem = (e->L.bytes + bsum_bytes <= smem_cap) ? 1 : 0;
+        smem = (A.blob_in_smem ? e->L.bytes : 0) + bsum_bytes;
+        kern = stats_on ? walk_compat_kernel<true> : walk_compat_kernel<false>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    } else {
+        std::vector<uint8_t> tab;
+        uint32_t stride = 0;
+        scale_constants(e, scales, n_scales, scale_type, tab, stride);
+        if ((rc = ensure(e, e->scale_tab, tab.size())) != SWK_OK) return rc;
+        CK(cudaMemcpyAsync(e->scale_tab.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream)); // `tab` is a local
+        A.scale_tab = static_cast<const uint8_t *>(e->scale_tab.p);
+        A.scale_stride = stride;
         const int vox = A.packed ? (use_slab ? VOX_SLAB : VOX_PACKED) : (A.fieldmap ? VOX_SPLIT : VOX_MASK);
         bool gruns = false; // does the timeline hold a run of gradient samples (swk_set_sequence: tl_run >= 2)?
         {
             const uint32_t *run = reinterpret_cast<const uint32_t *>(e->blob_h.data() + e->L.tl_run);
             for (uint32_t i = 0; i < e->L.n_tl; i++) gruns |= run[i] >= 2u;
         }
-#define SWK_PICK2(V, G) (A.record ? (stats_on ? walk_fast_kernel<true, true, V, G> : walk_fast_kernel<false, true, V, G>) \
-                                  : (stats_on ? walk_fast_kernel<true, false, V, G> : walk_fast_kernel<false, false, V, G>))
-#define SWK_PICK(V) (gruns ? SWK_PICK2(V, true) : SWK_PICK2(V, false))
-        kern = vox == VOX_PACKED ? SWK_PICK(VOX_PACKED) : (vox == VOX_SLAB ? SWK_PICK(VOX_SLAB) : (vox == VOX_SPLIT ? SWK_PICK(VOX_SPLIT) : SWK_PICK(VOX_MASK)));
-#undef SWK_PICK
-#undef SWK_PICK2
+        const size_t fixed_private = ((bsum_bytes + 15) & ~size_t(15)) + stride + (size_t)ES_FIELDS * 4 * kBlock;
+        if (fixed_private > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
+        // SHARED variant (walk_fast.cuh): 32 spins x G scales per block share the spins' normals.  Needs >= 2 scales and one spin order for all scales.
+        uint32_t G = (n_scales >= 2 && !(flags & SWK_RUN_NO_SHARE) && getenv("SWK_NO_SHARE") == nullptr) ? shared_group(n_scales) : 1u;
+        if (const char *ev = getenv("SWK_GROUP")) G = std::max(1, std::min(atoi(ev), (int)std::min<uint32_t>(n_scales, SWK_FAST_SHARED_MAXT / 32))); // tuning knob
+        const size_t nbuf_bytes = 2 * kBatch * 32 * sizeof(float4);
+        auto shared_bytes = [&](uint32_t g) { return ((bsum_bytes * g + 15) & ~size_t(15)) + (size_t)stride * g + (size_t)ES_FIELDS * 4 * 32 * g + nbuf_bytes; };
+        while (G > 1 && shared_bytes(G) > smem_cap) G--; // (many echoes x substrates: fewer scales per block)
+        const size_t fixed_shared = shared_bytes(G);
+        shared_variant = G >= 2;
+        A.blob_in_smem = (e->L.bytes + std::max(fixed_private, shared_variant ? fixed_shared : 0) <= smem_cap) ? 1 : 0;
+        smem_private = (A.blob_in_smem ? e->L.bytes : 0) + fixed_private;
+        kern_private = pick_fast<false>(vox, gruns, record, stats_on);
+        CK(cudaFuncSetAttribute(kern_private, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        if (shared_variant) {
+            A.group = G;
+            A.n_groups = (n_scales + G - 1) / G;
+            block = 32 * G;
+            smem = (A.blob_in_smem ? e->L.bytes : 0) + fixed_shared;
+            kern = pick_fast<true>(vox, gruns, record, stats_on);
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        } else {
+            kern = kern_private;
+            smem = smem_private;
+        }
     }
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    // blocks of a launch over thread slots [j_first, j_end)
+    auto grid_of = [&](uint32_t j0, uint32_t j1, bool shared) -> uint64_t {
+        const uint64_t n = j1 - j0;
+        return shared ? ((n + 31) / 32) * A.n_groups : ((n + kBlock - 1) / kBlock) * K;
+    };
+    if (grid_of(0, slice_len, shared_variant) > 0x7fffffffull || grid_of(0, slice_len, false) > 0x7fffffffull)
+        return fail(e, SWK_ERR_INVALID, "too many spins x scales for one launch");
+    // staging rows -> reference layouts, rows [r0, r1) of every scale (no-op when no per-spin output was requested)
+    auto unpack = [&](size_t r0, size_t r1, cudaStream_t st) -> cudaError_t {
+        if (!e->stage.p || r1 <= r0) return cudaSuccess;
+        const size_t total = (r1 - r0) * stage_row * K;
+        const unsigned g = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)e->sm_count * 32);
+        unpack_rows_kernel<<<g, 256, 0, st>>>(static_cast<const uint4 *>(e->stage.p), (uint32_t)stage_row, (uint32_t)E, S, r0, r1, (uint32_t)K,
+                                             static_cast<float *>(e->M1.p), static_cast<uint8_t *>(e->T.p), record ? nullptr : static_cast<float *>(e->XYZ1.p));
+        return cudaGetLastError();
+    };
 
-    if ((((uint64_t)slice_len + kBlock - 1) / kBlock) * K > 0x7fffffffull) return fail(e, SWK_ERR_INVALID, "too many spins x scales for one launch");
     CK(cudaEventRecord(e->ev0, e->stream));
     A.scan_first = 0;
     A.scan_end = A.n_scans;
     if (n_slices == 1) {
         A.j_first = 0;
         A.j_end = (uint32_t)S;
-        const uint64_t grid = ((S + kBlock - 1) / kBlock) * K;
         // ---- long runs (bSSFP: ~1000 TRs): pause at TR boundaries and re-sort the spins by their CURRENT voxel ----
         // The start order keeps the resident spins' voxels inside L2 only while they have not diffused apart: after n steps the
         // cloud has grown by ~2 sigma_vox sqrt(n) voxels per axis.  A pause every (35 / sigma_vox)^2 steps keeps that growth below
         // ~70 voxels (measured on C4: 2.26e11 steps/s at 60 TRs per leg, 2.13e11 at 125, 2.01e11 at 250, 1.65e11 without); it costs one 36-byte state record per walker and one radix sort.  Small FoV scales (sigma_vox > 2) touch the
-        // table at random whatever the order and are not re-binned.
+        // table at random whatever the order and are not re-binned; a z-slab table is cache resident whatever the order.
         uint32_t scans_per_leg = A.n_scans;
         bool per_scale = false;
         if (mode == SWK_MODE_FAST && A.order && !A.record && !(flags & SWK_RUN_NO_REBIN) && A.n_scans > 1) {
@@ -793,8 +979,10 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
                         sig_vox = std::max(sig_vox, sig[sub] * (double)e->dims[i] / ((double)e->fov[i] * (scale_type == SWK_SCALE_FOV ? (double)scales[k] : 1.)));
             const double n_rb = sig_vox > 0. ? (35. / sig_vox) * (35. / sig_vox) : 1e30;
             const double total = (double)A.n_scans * A.n_tp;
-            per_scale = scale_type == SWK_SCALE_FOV && K > 1; // the walks differ between scales only when the FoV is scaled
-            if (sig_vox <= 2. && total >= 2. * n_rb && (!per_scale || K * S <= (1ull << 29)))
+            // the walks differ between scales only when the FoV is scaled; the scale index is the top byte of the re-binning key, so
+            // runs with more than 256 scales share one order (that of scale 0: any order is valid, only locality suffers)
+            per_scale = scale_type == SWK_SCALE_FOV && K > 1 && K <= 256;
+            if (!use_slab && sig_vox <= 2. && total >= 2. * n_rb && (!per_scale || K * S <= (1ull << 29)))
                 scans_per_leg = (uint32_t)std::max(1., std::floor(n_rb / A.n_tp));
             if (const char *ev = getenv("SWK_REBIN_SCANS")) scans_per_leg = (uint32_t)std::max(1, atoi(ev)); // tuning knob
         }
@@ -813,7 +1001,8 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             for (uint32_t s0 = 0; s0 < A.n_scans; s0 += scans_per_leg) {
                 A.scan_first = s0;
                 A.scan_end = std::min(A.n_scans, s0 + scans_per_leg);
-                kern<<<(unsigned)grid, kBlock, smem, e->stream>>>(A);
+                if (s0 == 0) kern<<<(unsigned)grid_of(0, (uint32_t)S, shared_variant), block, smem, e->stream>>>(A);
+                else kern_private<<<(unsigned)grid_of(0, (uint32_t)S, false), kBlock, smem_private, e->stream>>>(A); // walkers resume at their own rounds
                 CK(cudaGetLastError());
                 if (A.scan_end == A.n_scans) break;
                 rebin_keys_kernel<<<(unsigned)((n_sort + 255) / 256), 256, 0, e->stream>>>(A.state_vox, A.state_b, (uint32_t)S, (uint32_t)n_seg, A.ny, A.nz,
@@ -830,26 +1019,33 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
                 extra_launches += 2;
             }
             extra_launches += (A.n_scans + scans_per_leg - 1) / scans_per_leg - 1; // n_launches below counts one walk launch per slice
+            CK(unpack(0, S, e->stream));
             CK(cudaStreamSynchronize(e->stream)); // order2 is freed on return
         } else {
-            kern<<<(unsigned)grid, kBlock, smem, e->stream>>>(A);
+            kern<<<(unsigned)grid_of(0, (uint32_t)S, shared_variant), block, smem, e->stream>>>(A);
             CK(cudaGetLastError());
+            CK(unpack(0, S, e->stream));
         }
     } else {
-        // slice i runs on compute stream i & 1 (tails overlap the next slice); its rows are downloaded as soon as it is done
+        // slice i runs on compute stream i & 1 (tails overlap the next slice); its rows are unpacked there and downloaded as soon as they are done
         const bool one_stream = getenv("SWK_ONE_CSTREAM") != nullptr; // tuning knob
         for (int c = 0; c < 2; c++) CK(cudaStreamWaitEvent(e->cstream[c], e->ev0, 0));
         for (uint32_t i = 0; i < n_slices; i++) {
             A.j_first = i * slice_len;
             A.j_end = (uint32_t)std::min<size_t>(S, (size_t)(i + 1) * slice_len);
-            const uint64_t grid = (((uint64_t)(A.j_end - A.j_first) + kBlock - 1) / kBlock) * K;
             cudaStream_t cs = e->cstream[one_stream ? 0 : (i & 1)];
-            kern<<<(unsigned)grid, kBlock, smem, cs>>>(A);
+            kern<<<(unsigned)grid_of(A.j_first, A.j_end, shared_variant), block, smem, cs>>>(A);
             CK(cudaGetLastError());
+            CK(unpack(A.j_first, A.j_end, cs)); // the sorted order is slice-major: slots [j_first, j_end) hold exactly the spins [j_first, j_end)
             CK(cudaEventRecord(e->ev_slice[i], cs));
         }
         CK(cudaStreamWaitEvent(e->stream, e->ev_slice[n_slices - 1], 0));
         CK(cudaStreamWaitEvent(e->stream, e->ev_slice[n_slices - 2], 0));
+    }
+    if (E * ns) {
+        const size_t n = K * E * ns * 4;
+        sums_to_double_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(static_cast<const unsigned long long *>(e->sums_fx.p), n, sums);
+        CK(cudaGetLastError());
     }
     CK(cudaEventRecord(e->ev1, e->stream));
     if (host && n_slices > 1) { // rows [j_first, j_end) of every scale: one strided copy per array and slice
@@ -857,21 +1053,12 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             const size_t r0 = (size_t)i * slice_len, r1 = std::min<size_t>(S, r0 + slice_len);
             const size_t HS = e->host_rows ? (size_t)e->host_rows : S, h0 = (e->host_rows ? (size_t)e->host_row_first : 0) + r0; // host pitch / first row
             CK(cudaStreamWaitEvent(e->dstream, e->ev_slice[i], 0));
-            if (host->M1 && e->M1.p) {
-                const size_t row = E * 3 * sizeof(float);
-                if (row) CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->M1) + h0 * row, HS * row, static_cast<char *>(e->M1.p) + r0 * row, S * row,
-                                              (r1 - r0) * row, K, cudaMemcpyDeviceToHost, e->dstream));
-            }
-            if (host->XYZ1 && e->XYZ1.p) {
-                const size_t row = e->trj * 3 * sizeof(float);
-                CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->XYZ1) + h0 * row, HS * row, static_cast<char *>(e->XYZ1.p) + r0 * row, S * row,
-                                     (r1 - r0) * row, K, cudaMemcpyDeviceToHost, e->dstream));
-            }
-            if (host->T && e->T.p) {
-                const size_t row = E;
-                if (row) CK(cudaMemcpy2DAsync(reinterpret_cast<char *>(host->T) + h0 * row, HS * row, static_cast<char *>(e->T.p) + r0 * row, S * row,
-                                              (r1 - r0) * row, K, cudaMemcpyDeviceToHost, e->dstream));
-            }
+            const size_t rows[3] = {E * 3 * sizeof(float), (size_t)e->trj * 3 * sizeof(float), E};
+            char *dst[3] = {reinterpret_cast<char *>(host->M1), reinterpret_cast<char *>(host->XYZ1), reinterpret_cast<char *>(host->T)};
+            const char *src[3] = {static_cast<const char *>(e->M1.p), static_cast<const char *>(e->XYZ1.p), static_cast<const char *>(e->T.p)};
+            for (int a = 0; a < 3; a++)
+                if (dst[a] && src[a] && rows[a])
+                    CK(copy_rows(dst[a] + h0 * rows[a], HS * rows[a], src[a] + r0 * rows[a], S * rows[a], (r1 - r0) * rows[a], K, e->mem_pitch, e->dstream));
         }
     }
     tr.mark("launches enqueued");
@@ -887,7 +1074,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
 
     e->n_scales = n_scales;
     e->out_flags = flags;
-    e->last_sums = A.sums;
+    e->last_sums = (E * ns) ? sums : nullptr;
     e->last_slices = n_slices;
     swk_stats &st = e->stats;
     st = swk_stats{};
@@ -899,9 +1086,11 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     st.lost = cnt[4];
     st.kernel_ms = ms;
     st.device_ms = ms_all;
-    st.n_launches = n_slices + extra_launches;
+    st.n_launches = n_slices + extra_launches + (e->stage.p ? n_slices : 0) + ((E * ns) ? 1 : 0);
     return SWK_OK;
 }
+
+extern "C" {
 
 int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags, double *d_sums)
 {
@@ -924,8 +1113,7 @@ int swk_download(swk_engine *e, float *M1, float *XYZ1, uint8_t *T)
         char *dst[3] = {reinterpret_cast<char *>(M1), reinterpret_cast<char *>(XYZ1), reinterpret_cast<char *>(T)};
         const char *src[3] = {static_cast<const char *>(e->M1.p), static_cast<const char *>(e->XYZ1.p), static_cast<const char *>(e->T.p)};
         for (int a = 0; a < 3; a++)
-            if (dst[a] && rows[a])
-                CK(cudaMemcpy2DAsync(dst[a] + h0 * rows[a], HS * rows[a], src[a], S * rows[a], S * rows[a], K, cudaMemcpyDeviceToHost, e->stream));
+            if (dst[a] && rows[a]) CK(copy_rows(dst[a] + h0 * rows[a], HS * rows[a], src[a], S * rows[a], S * rows[a], K, e->mem_pitch, e->stream));
     }
     CK(cudaStreamSynchronize(e->stream));
     return SWK_OK;
@@ -1046,7 +1234,7 @@ uint64_t swk_device_bytes(const swk_engine *e)
     if (!e) return 0;
     uint64_t n = 0;
     for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab})
+                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab})
         n += b->bytes;
     return n;
 }

@@ -1,25 +1,37 @@
 // spinwalk_b200/csrc/walk_fast.cuh — SWK_MODE_FAST walk kernel (the product path), sm_100a.
 //
-// Same stochastic process as the reference's time loop (src/sim/kernels.cu:107-232),
-// engineered for the B200 issue pipes instead of being a translation of it:
-//   * position = one 32-bit FIXED-POINT word per axis in grid units: voxel index in the high bits, FB fraction
-//     bits below.  A step is  pos += int(n * sigma)  done as one FFMA (magic-number rounding) + one IADD3;
-//     "did the voxel change" is (old ^ new) >> FB, so the common no-change step touches neither the index
-//     arithmetic nor memory, and there is no float<->int conversion (quarter-rate pipe) anywhere in the loop;
-//   * Philox4x32-10 with a fixed key: the ten round keys are immediates of the LOP3s (2 IMAD.WIDE + 2 LOP3 per
-//     round), Box-Muller on the MUFU pipe (lg2 / sqrt / sin / cos approx) — the random numbers of attempt n+1
-//     are generated between ISSUING the voxel gather of attempt n and CONSUMING it, so the gather latency
-//     (L2 ~250 cyc, HBM ~600+ cyc) overlaps ~65 independent instructions per warp;
-//   * one 4-byte gather per voxel change: the packed voxel word (FP32 field | 4-bit substrate id), read-only path;
-//   * per-thread time: lanes of a warp re-converge only at sequence events, so a lane that has to redraw
-//     (permeability rejection, kernels.cu:154-160) does not stall the other 31 per step;
-//   * 32-bit voxel indices (V < 2^32); registers kept low enough for >= 4 CTAs (32 warps) per SM.
+// Same stochastic process as the reference's time loop (src/sim/kernels.cu:107-232), engineered for the
+// B200 issue pipes — the launch is ISSUE bound once the voxel table is cache resident (ncu, profiles/), so the design
+// minimises warp-instructions per attempted step:
+//   * SHARED RANDOM STREAM.  The reference re-seeds seed+spin for every scale (kernels.cu:77-88): all FoV scales of a spin
+//     replay the SAME displacement stream.  A block therefore walks 32 spins x G scales (one warp per scale, one lane per
+//     spin) and generates each spin's normals ONCE per block — Philox4x32-10 + Box-Muller on the MUFU pipe, 16 rounds at a
+//     time into shared memory, double buffered — instead of once per (spin, scale): ~47 of the ~90 instructions an attempt
+//     used to cost are paid once per G walkers.  (Runs with one scale, and legs resumed after a re-binning pause, use the
+//     PRIVATE variant: every thread generates its own normals; same numbers, same results.)
+//   * ROUND r of spin j uses normals (j, r): Philox block r >> 1, half r & 1.  A walker executes one attempt per round
+//     while it has steps left in its current segment (a segment = the steps up to the next sequence event); when the segment
+//     is complete it waits for the next round that is a multiple of kSync and runs the event there.  Which rounds a walker
+//     uses therefore depends on its own history only: results are independent of warp / block composition (shard, slice,
+//     re-binning and sort invariance are bitwise, tested), and skipped normals are independent of everything the walker used.
+//   * the attempt itself is straight-line predicated code (no per-lane branches but three rare ones: FoV wall, substrate
+//     change, loss): position = one 32-bit FIXED-POINT word per axis (voxel << FB | fraction), a step is one FFMA
+//     (magic-number rounding) + one IADD3 per axis, "did the voxel change" is one integer compare of the table index, the
+//     voxel fetch is one predicated 4-byte gather of the packed voxel word (FP32 field whose 4 low mantissa bits are the
+//     substrate id) from the read-only path, accept / reject is a select;
+//   * 32-bit voxel indices (V < 2^32); ensemble sums in integer fixed point (bit-reproducible, order independent).
 #pragma once
 
 #include "walk_kernel.cuh"
 
 #ifndef SWK_FAST_MIN_BLOCKS
-#define SWK_FAST_MIN_BLOCKS 5 // 48 registers: 40 warps per SM (measured best on the C2 mix of scales, profiles/)
+#define SWK_FAST_MIN_BLOCKS 5 // PRIVATE variant: 48 registers, 40 warps per SM
+#endif
+#ifndef SWK_FAST_SHARED_MAXT
+#define SWK_FAST_SHARED_MAXT 320 // SHARED variant: at most 10 scales (warps) per block
+#endif
+#ifndef SWK_FAST_SHARED_MINB
+#define SWK_FAST_SHARED_MINB 4   // ... and at most 65536 / (4 x 320) = 51 -> 48 registers: 40 warps per SM
 #endif
 
 namespace swk {
@@ -31,8 +43,8 @@ __device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ft
 
 // Philox4x32-10 (Salmon et al., SC'11) with a FIXED key so that the ten round keys are immediates of the
 // LOP3s (2 IMAD.WIDE + 2 LOP3 per round, no key registers).  The run's seed lives in the counter instead:
-//   counter = (attempt counter, seed[31:0], global spin id, stream tag << 30 | seed[61:32])
-// Philox is a bijection of the counter for any key, so distinct (seed, spin, attempt, stream) tuples
+//   counter = (block counter, seed[31:0], global spin id, stream tag << 30 | seed[61:32])
+// Philox is a bijection of the counter for any key, so distinct (seed, spin, block, stream) tuples
 // give distinct, decorrelated 128-bit blocks.  Every scale replays the same stream, like the reference
 // re-seeding seed+spin for each scale (kernels.cu:77-88).
 __device__ __forceinline__ uint4 philox_fixed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
@@ -51,9 +63,8 @@ __device__ __forceinline__ uint4 philox_fixed(uint32_t c0, uint32_t c1, uint32_t
     return make_uint4(c0, c1, c2, c3);
 }
 
-// Philox2x32-10 (same paper) for the permeability uniform (kernels.cu:154): one 32-bit word is needed per test, and the test runs
-// whenever ANY lane of the warp changes substrate with 0 < P < 1 — half the multiplies of a 4x32 block (10 IMAD.WIDE + 10 LOP3).
-//   counter = (attempt index of the walker, global spin id); key = a 32-bit fold of the run's seed (engine.cu), whose ten round keys
+// Philox2x32-10 (same paper) for the permeability uniform (kernels.cu:154): one 32-bit word per test.
+//   counter = (round index of the walker, global spin id); key = a 32-bit fold of the run's seed (engine.cu), whose ten round keys
 //   key + r * 0x9E3779B9 arrive as kernel parameters, i.e. as constant-bank operands of the LOP3s.
 // A different generator AND key than the displacement stream: the two are independent (the reference draws both from copies of
 // one minstd stream).
@@ -68,25 +79,9 @@ __device__ __forceinline__ uint32_t philox2x32_10(uint32_t c0, uint32_t c1, cons
     return c0;
 }
 
-// three N(0,1) from 128 random bits: Box-Muller, 23-bit uniforms, hardware transcendental approximations.
-// |n| <= sqrt(2 ln 2^23) = 5.65 by construction (what bounds the fixed-point step below).
-__device__ __forceinline__ void normals3_fast(const uint4 r, float &n0, float &n1, float &n2)
-{
-    const float kNeg2Ln2 = -1.3862943611198906f, k2Pi = 6.283185307179586f;
-    const float ua = 2.0f - __uint_as_float((r.x >> 9) | 0x3f800000u); // (0,1]
-    const float ub = 2.0f - __uint_as_float((r.z >> 9) | 0x3f800000u);
-    const float ta = fmaf(__uint_as_float((r.y >> 9) | 0x3f800000u), k2Pi, -k2Pi); // [0, 2 pi)
-    const float tb = fmaf(__uint_as_float((r.w >> 9) | 0x3f800000u), k2Pi, -k2Pi);
-    const float ra = mufu_sqrt(kNeg2Ln2 * mufu_lg2(ua));
-    const float rb = mufu_sqrt(kNeg2Ln2 * mufu_lg2(ub));
-    n0 = ra * mufu_cos(ta);
-    n1 = ra * mufu_sin(ta);
-    n2 = rb * mufu_cos(tb);
-}
-
 // six N(0,1) from ONE 128-bit Philox block: three Box-Muller pairs.  Pair i takes its radius uniform from the top 23 bits
 // of word i (r.x / r.y / r.z) and its 19-bit angle uniform from the remaining 9 bits of that word followed by a 10-bit field
-// of r.w — 126 of the 128 bits, no bit used twice.  |n| <= sqrt(2 ln 2^23) = 5.65.  One block feeds TWO attempts of the walk.
+// of r.w — 126 of the 128 bits, no bit used twice.  |n| <= sqrt(2 ln 2^23) = 5.65.  One block feeds TWO rounds of the walk.
 //   `one` holds 0x3f800000 in a REGISTER (it arrives as a kernel argument so that ptxas cannot turn it back into an
 //   immediate): (x & 0x007ffff0) | one is then a single LOP3 instead of two.
 __device__ __forceinline__ uint32_t and_or(const uint32_t x, const uint32_t one)
@@ -112,7 +107,7 @@ __device__ __forceinline__ void normals6_fast(const uint4 r, const uint32_t one,
 }
 
 // ---- fixed-point grid coordinates -------------------------------------------------------------------------------
-// pos = voxel << FB | fraction, FB chosen per launch-block (per scale) on the host side of the kernel:
+// pos = voxel << FB | fraction, FB chosen per scale on the host (engine.cu scale_constants):
 //   (a) 5.65 sigma_vox 2^FB < 2^22   so that the magic-number rounding of the step is exact to one unit,
 //   (b) (n + 1) 2^FB + 2^22 <= 2^32  so that a step across the far wall cannot wrap to a valid position;
 // a step below 0 wraps to >= 2^32 - 2^22, which (b) keeps above every valid position: both walls are caught by ONE
@@ -125,8 +120,8 @@ __device__ __forceinline__ uint32_t fx_step(uint32_t pos, float n, float sg)
     return pos + (uint32_t)__float_as_int(fmaf(n, sg, kMagic)) - kMagicBits;
 }
 
-// FoV boundary of one axis (rare; out of line).  kernels.cu:133-136.  `q` is the tentative position, already outside [0, n).
-__device__ __noinline__ uint32_t fov_boundary(uint32_t q, const uint32_t p, const uint32_t n, const uint32_t fb, const int cross)
+// FoV boundary of one axis (rare).  kernels.cu:133-136.  `q` is the tentative position, already outside [0, n).
+__device__ __forceinline__ uint32_t fov_boundary(uint32_t q, const uint32_t p, const uint32_t n, const uint32_t fb, const int cross)
 {
     const uint32_t span = n << fb;
     if (cross) { // periodic: re-enter from the other side (single wrap, like the reference)
@@ -151,351 +146,480 @@ __device__ __forceinline__ uint32_t ldg_voxel(const uint32_t *p)
 }
 
 // VOX selects how a voxel is fetched: 0 = mask only (no fieldmap), 1 = mask byte + FP32 field (two gathers issued
-// together), 2 = one packed 32-bit word (field with its 4 low mantissa bits replaced by the substrate id).
-// 3 = the packed word of a phantom that is invariant along z (every cylinder phantom), fetched from its [nx][ny] slab: the same
-// words as variant 2 from a table nz times smaller (opt-in: SWK_RUN_ZSLAB, engine.cu run_impl).
+// together), 2 = one packed 32-bit word (the FP32 field rounded to the nearest value whose 4 low mantissa bits spell the
+// substrate id; engine.cu pack_word), 3 = the packed word of a phantom that is invariant along z (every cylinder phantom),
+// fetched from its [nx][ny] slab: the same words as variant 2 from a table nz times smaller (L1/L2 resident).
 enum { VOX_MASK = 0, VOX_SPLIT = 1, VOX_PACKED = 2, VOX_SLAB = 3 };
 
-// GRUNS: the sequence holds runs of gradient samples (taken inside the inner loop); sequences without them get a kernel without that code.
+constexpr uint32_t kSync = 8;   // a walker runs its sequence events at rounds that are multiples of kSync (see the file header)
+constexpr uint32_t kBatch = 16; // SHARED variant: rounds of normals generated per barrier (32 spins x 16 rounds = 256 Philox blocks)
+
+// Per-scale constants, computed once per run on the host in double precision (engine.cu scale_constants) and staged in shared
+// memory by the blocks that walk the scale.  float sgt[3 * n_sub] follows at byte offset sgt_off: the step sigma per (substrate,
+// axis) in fixed-point units.
+struct ScaleConst {
+    uint32_t fb;            // fraction bits of the fixed-point position
+    float fscale, gscale, lin_pc; // FoV scale (monte_carlo.cu:278-280), gradient scale (:288-290), linear phase cycling (:303)
+    float umk[3];           // degrees of phase per (mT/m x fixed-point unit) and axis (gradient runs, kernels.cu:185)
+    uint32_t sgt_off;       // byte offset of sgt from the start of this record
+    double unit_m[3];       // metres per fixed-point unit at this scale (events and outputs)
+    double pos_k[3];        // fixed-point units per UNSCALED metre of XYZ0 (positions and FoV scale together)
+    double pos_hi[3];       // n 2^FB - 1: spins exactly on the far wall start in the last voxel
+};
+
+enum : uint32_t { SEG_START = 0u, SEG_EVENT = 1u, SEG_RUN0 = 2u, SEG_RUN1 = 3u, SEG_TAIL = 4u };
+
+// SHARED variant: normals of rounds [r0, r0 + kBatch) of a block's 32 spins.  Thread t makes Philox block (r0 >> 1) + (t >> 5) of ITS lane's
+// spin and stores the two rounds it feeds as float4 (x, y, z step normals, permeability uniform) at buf[round][lane].  Out of line on purpose:
+// its ~30 temporaries must not compete with the registers of the round loop.
+__device__ __noinline__ void generate_normals(float4 *buf, const uint32_t r0, const uint32_t spin_no, const uint32_t seed_lo, const uint32_t seed_hi_walk,
+                                              const uint32_t one_bits, const uint32_t *perm_key /* nullptr: no permeability draws needed */)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t i = threadIdx.x; i < 32u * (kBatch / 2u); i += blockDim.x) {
+        const uint32_t h = i >> 5; // (i & 31) == lane: blockDim is a multiple of 32
+        float a0, a1, a2, b0, b1, b2;
+        normals6_fast(philox_fixed((r0 >> 1) + h, seed_lo, spin_no, seed_hi_walk), one_bits, a0, a1, a2, b0, b1, b2);
+        float ua = 0.f, ub = 0.f;
+        if (perm_key) { // some 0 < P_XY < 1: the permeability uniforms of the two rounds ride along
+            uint32_t key[10];
+#pragma unroll
+            for (int q = 0; q < 10; q++) key[q] = perm_key[q];
+            ua = u01_open1(philox2x32_10(r0 + 2u * h, spin_no, key));
+            ub = u01_open1(philox2x32_10(r0 + 2u * h + 1u, spin_no, key));
+        }
+        buf[(2u * h) * 32u + lane] = make_float4(a0, a1, a2, ua);
+        buf[(2u * h + 1u) * 32u + lane] = make_float4(b0, b1, b2, ub);
+    }
+}
+
+// Sequence state of a walker that is only touched at events lives in shared memory (structure of arrays, one word per thread and
+// field) so that the registers of the round loop hold nothing but the walk itself.
+enum : uint32_t { ES_M0 = 0u, ES_M1, ES_M2, ES_SCAN, ES_EV, ES_SEG, ES_TSTOP, ES_TOLD, ES_RF, ES_TE, ES_DEPH, ES_GFIRST, ES_RUNLEN, ES_FIELDS };
+
+// ======================================= events (out of line) =======================================
+// Cold per-walker context of advance_walker, built once per thread (lives in local memory: it is only read at events).
+struct AdvCtx {
+    const WalkArgs *A;     // the kernel's parameter block
+    const uint8_t *B;      // sequence tables (shared memory when they fit, else global)
+    const ScaleConst *SC;  // this walker's scale
+    uint32_t *es;          // this thread's event state, field f at es[f * nthr]
+    long long *bsum;       // block sums of this walker's scale
+    uint4 *stage;          // this walker's staging row, or nullptr
+    size_t st_idx;         // index into the pause-state arrays
+    uint32_t spin_no, nthr, n_bsum;
+};
+struct AdvOut {
+    float acc;
+    int rem;
+    uint32_t cnt_grad, flags;
+};
+enum : uint32_t { WF_LOST = 1u, WF_DONE = 2u, WF_GRUN = 4u, WF_FRESH = 8u };
+
+// Called at a round that is a multiple of kSync by a walker whose segment is complete (rem == 0): runs the sequence events that are due
+// (kernels.cu:175-215, 226-231, 110-126) and sets up the next segment; `r_next` is the first round the walker will use afterwards.
+// Out of line on purpose: the event arithmetic (sincos / exp / FP64) must not compete with the registers of the round loop.
 template <bool STATS, bool RECORD, int VOX, bool GRUNS>
-__global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(const __grid_constant__ WalkArgs A)
+__device__ __noinline__ AdvOut advance_walker(const AdvCtx *cx, const uint32_t p0, const uint32_t p1, const uint32_t p2, const uint32_t wcur, float acc,
+                                              uint32_t cnt_grad, uint32_t flags, const uint32_t r_next)
+{
+    const WalkArgs &A = *cx->A;
+    const BlobLayout &L = A.L;
+    const uint8_t *B = cx->B;
+    const ScaleConst &SC = *cx->SC;
+    uint32_t *es = cx->es;
+    const uint32_t nthr = cx->nthr;
+    uint4 *stage = cx->stage;
+    const uint32_t n_tp = A.n_tp;
+    const int32_t  *tl_time = blob_ptr<int32_t>(B, L.tl_time);
+    const uint32_t *tl_mask = blob_ptr<uint32_t>(B, L.tl_mask), *tl_run = blob_ptr<uint32_t>(B, L.tl_run);
+    const float *gtx = blob_ptr<float>(B, L.gx), *gty = blob_ptr<float>(B, L.gy), *gtz = blob_ptr<float>(B, L.gz);
+    const float *tT1 = blob_ptr<float>(B, L.T1s), *tT2 = blob_ptr<float>(B, L.T2s);
+    const uint32_t ts = (VOX == VOX_PACKED || VOX == VOX_SLAB) ? (wcur & 15u) : wcur; // the substrate does not change during events
+    const bool lost = (flags & WF_LOST) != 0u;
+
+    float m[3] = {__uint_as_float(es[ES_M0 * nthr]), __uint_as_float(es[ES_M1 * nthr]), __uint_as_float(es[ES_M2 * nthr])};
+    uint32_t scan = es[ES_SCAN * nthr], ev = es[ES_EV * nthr], seg = es[ES_SEG * nthr], t_stop = es[ES_TSTOP * nthr], t_old = es[ES_TOLD * nthr];
+    uint32_t cur_rf = es[ES_RF * nthr], cur_te = es[ES_TE * nthr], cnt_deph = es[ES_DEPH * nthr], grad_first = es[ES_GFIRST * nthr], run_len = es[ES_RUNLEN * nthr];
+    const float gscale = SC.gscale;
+    int rem = 0;
+    bool finished = false;
+    for (;;) {
+        if (lost) { // abandoned (kernels.cu:155-159)
+            if (scan + 1 != A.n_scans) cur_te = 0; // no echo of the last scan was written
+            finished = true;
+            break;
+        }
+        if (seg == SEG_EVENT) { // events of timepoint tl_time[ev], in the reference's order (kernels.cu:175-215)
+            const uint32_t mask_ev = tl_mask[ev];
+            const uint32_t tp = (uint32_t)tl_time[ev];
+            if (mask_ev & EV_DEPH) { // kernels.cu:175-178
+                acc += (float)cx->spin_no * blob_ptr<float>(B, L.deph_deg)[cnt_deph] / (float)A.n_spins_global;
+                cnt_deph++;
+            }
+            if (mask_ev & EV_GRAD) { // kernels.cu:181-187
+                const float Gx = __fmul_rn(gtx[cnt_grad], gscale), Gy = __fmul_rn(gty[cnt_grad], gscale), Gz = __fmul_rn(gtz[cnt_grad], gscale); // monte_carlo.cu:288-290
+                const double X = (double)p0 * SC.unit_m[0], Y = (double)p1 * SC.unit_m[1], Z = (double)p2 * SC.unit_m[2];
+                double g = __fma_rn((double)Gz, Z, __fma_rn((double)Gx, X, __dmul_rn((double)Gy, Y)));
+                g = g * 1e-3 * (double)A.timestep_us * 1e-6 * kGamma;
+                acc = (float)__fma_rn(g, kRad2Deg, (double)acc);
+                cnt_grad++;
+            }
+            if (mask_ev & EV_RF) { // kernels.cu:190-199
+                const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
+                dephase_relax(m, acc, tT1[ts], tT2[ts], dt_s);
+                float rr[3];
+                xrot_withphase(blob_ptr<float>(B, L.rf_s)[cur_rf], blob_ptr<float>(B, L.rf_c)[cur_rf], blob_ptr<float>(B, L.rf_ph)[cur_rf], m, rr);
+                m[0] = rr[0]; m[1] = rr[1]; m[2] = rr[2];
+                acc = 0.f;
+                t_old = tp;
+                cur_rf++;
+            }
+            if ((mask_ev & EV_ECHO) && scan + 1 == A.n_scans) { // kernels.cu:202-215
+                const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
+                dephase_relax(m, acc, tT1[ts], tT2[ts], dt_s);
+                if (stage) stage[cur_te] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts);
+                acc = 0.f;
+                t_old = tp;
+                if (A.sums_fx) echo_sums_add(cx->bsum, cur_te * L.n_sub + ts, m);
+                cur_te++;
+            }
+            ev++;
+        } else if (seg == SEG_RUN0) { // the plain steps before a run of gradient samples are done: now the run itself
+            seg = SEG_RUN1;
+            flags |= WF_GRUN;
+            grad_first = cnt_grad;
+            rem = (int)run_len;
+            t_stop += run_len;
+            break;
+        } else if (seg == SEG_RUN1) {
+            flags &= ~WF_GRUN;
+            cnt_grad = grad_first + run_len;
+            ev += run_len;
+        } else {
+            if (seg == SEG_TAIL) { // end of TR (kernels.cu:226-231)
+                const float dt_s = (float)((double)((n_tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
+                dephase_relax(m, acc, tT1[ts], tT2[ts], dt_s);
+                scan++;
+                if (scan >= A.scan_end) { finished = true; break; }
+            }
+            { // start of a TR: phase cycling + first RF (kernels.cu:110-126)
+                float ph = (float)((double)(A.rf_ph0 + (float)scan * SC.lin_pc) + (double)(scan * (scan + 1u)) / 2.0 * (double)A.quad_pc);
+                while (ph > 360.0) ph = (float)(ph - 360.0);
+                while (ph < 0) ph = (float)(ph + 360.0);
+                float rr[3];
+                xrot_withphase(A.s, A.c, ph, m, rr);
+                m[0] = rr[0]; m[1] = rr[1]; m[2] = rr[2];
+                t_stop = 0; t_old = 0; ev = 0;
+                cur_rf = 1; cur_te = 0; cnt_deph = 0; cnt_grad = 0;
+                acc = 0.f;
+                if (STATS) flags |= WF_FRESH;
+            }
+        }
+        // ---- next segment: the steps up to and including the next entry's timepoint, or the plain steps before a run of
+        //      gradient-only samples at consecutive timepoints (a PGSE lobe: one sample per step), or the rest of the TR ----
+        const uint32_t ev_time = ev < L.n_tl ? (uint32_t)tl_time[ev] : n_tp;
+        uint32_t stop;
+        if (ev >= L.n_tl || ev_time >= n_tp) { stop = n_tp; seg = SEG_TAIL; }
+        else if (GRUNS && tl_run[ev] >= 2u) { stop = ev_time; seg = SEG_RUN0; run_len = min(tl_run[ev], n_tp - ev_time); }
+        else { stop = ev_time + 1u; seg = SEG_EVENT; }
+        rem = (int)(stop - t_stop);
+        t_stop = stop;
+        if (rem > 0) break;
+    }
+    if (finished) { // this launch's scans are complete (or the walker was abandoned)
+        flags |= WF_DONE;
+        rem = 0;
+        if (A.scan_end < A.n_scans) { // pause at a TR boundary: the round index is the whole RNG state
+            A.state_a[cx->st_idx] = make_uint4(p0, p1, p2, r_next);
+            A.state_b[cx->st_idx] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts | ((lost ? 1u : 0u) << 8));
+            A.state_vox[cx->st_idx] = ((p0 >> SC.fb) * A.ny + (p1 >> SC.fb)) * A.nz + (p2 >> SC.fb);
+        } else if (stage) {
+            // echoes that never fired (beyond the TR, or after the walker was abandoned) read 0, like the reference's zero-initialised
+            // outputs (monte_carlo.cu:256,259-260); the final position is the last committed one (kernels.cu:220-221)
+            for (uint32_t e = cur_te; e < A.n_te; e++) stage[e] = make_uint4(0u, 0u, 0u, 0u);
+            if (!RECORD) stage[A.n_te] = make_uint4(__float_as_uint((float)((double)p0 * SC.unit_m[0])), __float_as_uint((float)((double)p1 * SC.unit_m[1])),
+                                                    __float_as_uint((float)((double)p2 * SC.unit_m[2])), lost ? 1u : 0u);
+        }
+    } else {
+        es[ES_M0 * nthr] = __float_as_uint(m[0]); es[ES_M1 * nthr] = __float_as_uint(m[1]); es[ES_M2 * nthr] = __float_as_uint(m[2]);
+        es[ES_SCAN * nthr] = scan; es[ES_EV * nthr] = ev; es[ES_SEG * nthr] = seg; es[ES_TSTOP * nthr] = t_stop; es[ES_TOLD * nthr] = t_old;
+        es[ES_RF * nthr] = cur_rf; es[ES_TE * nthr] = cur_te; es[ES_DEPH * nthr] = cnt_deph; es[ES_GFIRST * nthr] = grad_first; es[ES_RUNLEN * nthr] = run_len;
+    }
+    AdvOut o;
+    o.acc = acc; o.rem = rem; o.cnt_grad = cnt_grad; o.flags = flags;
+    return o;
+}
+
+// GRUNS: the sequence holds runs of gradient samples (taken inside the round); sequences without them get a kernel without that code.
+// SHARED: block = 32 spins x A.group scales sharing the spins' normals through shared memory; else block = kBlock spins of one scale.
+template <bool STATS, bool RECORD, int VOX, bool GRUNS, bool SHARED>
+__global__ void __launch_bounds__(SHARED ? SWK_FAST_SHARED_MAXT : kBlock, SHARED ? SWK_FAST_SHARED_MINB : SWK_FAST_MIN_BLOCKS)
+walk_fast_kernel(const __grid_constant__ WalkArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlobLayout &L = A.L;
+    const uint32_t nthr = blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
 
-    // ---- stage the sequence tables in shared memory ----
+    // ---- shared memory: [sequence tables] [block sums, int64] [scale constants of this block's scales] [event state] [normals, SHARED] ----
     const uint8_t *B = A.blob;
-    uint32_t smem_used = 0;
+    uint32_t off = 0;
     if (A.blob_in_smem) {
         const uint32_t nw = L.bytes / 4;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(A.blob);
         uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
-        for (uint32_t i = threadIdx.x; i < nw; i += kBlock) dst[i] = __ldg(src + i);
+        for (uint32_t i = threadIdx.x; i < nw; i += nthr) dst[i] = __ldg(src + i);
         B = smem;
-        smem_used = L.bytes;
+        off = L.bytes; // multiple of 16
     }
-    float *bsum = reinterpret_cast<float *>(smem + smem_used);
-    const uint32_t n_bsum = A.sums ? A.n_te * L.n_sub * 4u : 0u;
-    // per-substrate step sigma in fixed-point grid units for this block's scale: sgt[sub][axis]
-    float *sgt = bsum + n_bsum;
-    for (uint32_t i = threadIdx.x; i < n_bsum; i += kBlock) bsum[i] = 0.f;
+    const uint32_t n_grp = SHARED ? A.group : 1u;                   // scales walked by this block
+    const uint32_t n_bsum = A.sums_fx ? A.n_te * L.n_sub * 4u : 0u; // entries per scale
+    long long *bsum = reinterpret_cast<long long *>(smem + off);
+    off += (n_bsum * n_grp * 8u + 15u) & ~15u;
+    uint8_t *sct = smem + off;
+    off += A.scale_stride * n_grp;
+    uint32_t *es = reinterpret_cast<uint32_t *>(smem + off) + threadIdx.x; // field f of this thread: es[f * nthr]
+    off += ES_FIELDS * 4u * nthr;                                          // (nthr is a multiple of 32: stays 16-byte aligned)
+    float4 *nbuf = reinterpret_cast<float4 *>(smem + off);                 // [2][kBatch][32], SHARED only
 
-    const uint32_t k = blockIdx.x % A.n_scales;
-    const float scale = __ldg(A.scales + k);
-    float fscale = 1.f, gscale = 1.f, lin_pc = A.lin_pc;
-    if (A.scale_type == SWK_SCALE_FOV) fscale = scale;
-    else if (A.scale_type == SWK_SCALE_GRADIENT) gscale = scale;
-    else if (A.scale_type == SWK_SCALE_PHASE_CYCLING) lin_pc = __fmul_rn(A.lin_pc, scale); // monte_carlo.cu:303
-
-    const uint32_t n3[3] = {A.nx, A.ny, A.nz};
-    double inv_h[3]; // grid units per metre at scale 1
-#pragma unroll
-    for (int i = 0; i < 3; i++) inv_h[i] = (double)n3[i] / (double)A.fov[i];
-
-    // ---- fraction bits of this block's scale (block-uniform) ----
-    uint32_t fb;
+    // ---- which (spin, scale) ----
+    uint32_t k, j, k_loc, k_first;
+    if (SHARED) {
+        k_first = (blockIdx.x % A.n_groups) * A.group;
+        k_loc = threadIdx.x >> 5;
+        k = k_first + k_loc;
+        j = A.j_first + (blockIdx.x / A.n_groups) * 32u + lane;
+    } else {
+        k_loc = 0u;
+        k = k_first = blockIdx.x % A.n_scales;
+        j = A.j_first + (blockIdx.x / A.n_scales) * kBlock + threadIdx.x;
+    }
+    for (uint32_t i = threadIdx.x; i < n_bsum * n_grp; i += nthr) bsum[i] = 0;
     {
-        const double *tsig = blob_ptr<double>(A.blob, L.sigma);
-        double smax = 0.;
-        for (uint32_t s = 0; s < L.n_sub; s++)
-            for (int i = 0; i < 3; i++) smax = fmax(smax, tsig[s] * inv_h[i] / (double)fscale);
-        const uint32_t nmax = max(n3[0], max(n3[1], n3[2]));
-        int f = 22;
-        while (f > 0 && ((double)(nmax + 1u) * (double)(1u << f) + 4194304. > 4294967296.)) f--; // (b)
-        while (f > 0 && 5.7 * smax * (double)(1u << f) >= 4194304.) f--;                           // (a)
-        fb = (uint32_t)f;
-        for (uint32_t i = threadIdx.x; i < 3u * L.n_sub; i += kBlock) {
-            const uint32_t ax = i % 3u;
-            const double ih = ax == 0 ? inv_h[0] : (ax == 1 ? inv_h[1] : inv_h[2]);
-            sgt[i] = (float)(tsig[i / 3u] * ih / (double)fscale * (double)(1u << f));
-        }
-        if (threadIdx.x < 3u) { // metres per fixed-point unit x (1e-3 dt 1e-6 gamma 180/pi), kernels.cu:185
-            const double ih = threadIdx.x == 0 ? inv_h[0] : (threadIdx.x == 1 ? inv_h[1] : inv_h[2]);
-            sgt[3u * L.n_sub + threadIdx.x] = (float)((double)fscale / (ih * (double)(1u << f)) * 1e-3 * (double)A.timestep_us * 1e-6 * kGamma * kRad2Deg);
-        }
+        const uint32_t wps = A.scale_stride / 4u; // words per scale record
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.scale_tab) + (size_t)k_first * wps;
+        for (uint32_t i = threadIdx.x; i < wps * n_grp; i += nthr)
+            reinterpret_cast<uint32_t *>(sct)[i] = (k_first + i / wps) < A.n_scales ? __ldg(src + i) : 0u;
     }
     __syncthreads();
-    // metres per fixed-point unit at this scale (events and outputs only)
-    const double unit_m[3] = {(double)fscale / (inv_h[0] * (double)(1u << fb)), (double)fscale / (inv_h[1] * (double)(1u << fb)),
-                              (double)fscale / (inv_h[2] * (double)(1u << fb))};
 
-    const int32_t  *tl_time = blob_ptr<int32_t>(B, L.tl_time);
-    const uint32_t *tl_mask = blob_ptr<uint32_t>(B, L.tl_mask), *tl_run = blob_ptr<uint32_t>(B, L.tl_run);
+    const bool spin_ok = j < A.j_end;
+    const bool valid = spin_ok && k < A.n_scales;
+    const uint32_t kc = k < A.n_scales ? k : k_first; // a padding warp of the last group reads valid constants and walks nothing
+    const ScaleConst &SC = *reinterpret_cast<const ScaleConst *>(sct + (size_t)(kc - k_first) * A.scale_stride);
+    const float *sgt = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(&SC) + SC.sgt_off);
+    const uint32_t fb = SC.fb;
+
     const float *gtx = blob_ptr<float>(B, L.gx), *gty = blob_ptr<float>(B, L.gy), *gtz = blob_ptr<float>(B, L.gz);
-    const float *umk = sgt + 3u * L.n_sub; // degrees of phase per (mT/m x fixed-point unit) and axis, for gradient runs
-    const float *tT1 = blob_ptr<float>(B, L.T1s), *tT2 = blob_ptr<float>(B, L.T2s), *tpXY = blob_ptr<float>(B, L.pXY);
+    const float *tpXY = blob_ptr<float>(B, L.pXY);
 
-    // ---- which spin ----
-    const uint32_t j = A.j_first + (blockIdx.x / A.n_scales) * kBlock + threadIdx.x;
-    bool alive = j < A.j_end;
-    const uint32_t jl = alive ? (A.order ? __ldg(A.order + (A.order_per_scale ? (size_t)k * A.n_local : 0) + j) : j) : 0u;
+    const uint32_t jl = spin_ok ? (A.order ? __ldg(A.order + ((!SHARED && A.order_per_scale) ? (size_t)k * A.n_local : 0) + j) : j) : 0u;
     const uint32_t spin_no = A.spin_first + jl; // GLOBAL spin id: RNG key and dephasing term
+    const uint32_t n0 = A.nx, n1 = A.ny, n2 = A.nz;
+    const size_t st_idx = (size_t)kc * A.n_local + jl;
 
-    float m[3] = {0.f, 0.f, 1.f};
-    uint32_t p0, p1, p2; // fixed-point position
+    // ---- walker state ----
+    uint32_t p0 = 0, p1 = 0, p2 = 0; // fixed-point position
+    uint32_t r_first = 0;            // first round of this launch (a multiple of kSync)
+    bool lost = false, lost_before = false;
+    uint32_t ts_saved = 0;
     {
-        uint32_t pp[3];
+        float m[3] = {0.f, 0.f, 1.f};
+        if (valid) {
+            if (A.scan_first == 0) {
+                uint32_t pp[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            float x0 = 0.f;
-            if (alive) {
-                x0 = __ldg(A.xyz0 + 3 * (size_t)jl + i);
-                if (A.m0) m[i] = __ldg(A.m0 + 3 * (size_t)jl + i);
+                for (int i = 0; i < 3; i++) {
+                    const float x0 = __ldg(A.xyz0 + 3 * (size_t)jl + i);
+                    if (A.m0) m[i] = __ldg(A.m0 + 3 * (size_t)jl + i);
+                    pp[i] = (uint32_t)fmin(fmax((double)x0 * SC.pos_k[i], 0.), SC.pos_hi[i]);
+                }
+                p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
+            } else { // resuming after a re-binning pause (engine.cu run_impl): position, round, magnetisation, substrate come back from the state arrays
+                const uint4 sa = A.state_a[st_idx], sb = A.state_b[st_idx];
+                p0 = sa.x; p1 = sa.y; p2 = sa.z; r_first = sa.w;
+                m[0] = __uint_as_float(sb.x); m[1] = __uint_as_float(sb.y); m[2] = __uint_as_float(sb.z);
+                ts_saved = sb.w & 0xffu;
+                lost = lost_before = (sb.w & 0x100u) != 0u; // abandoned in an earlier launch (already counted there)
             }
-            double g = (double)x0 * inv_h[i] * (double)(1u << fb);
-            const double hi = (double)n3[i] * (double)(1u << fb) - 1.; // spins exactly on the far wall start in the last voxel
-            g = fmin(fmax(g, 0.), hi);
-            pp[i] = (uint32_t)g;
         }
-        p0 = pp[0]; p1 = pp[1]; p2 = pp[2];
+        es[ES_M0 * nthr] = __float_as_uint(m[0]); es[ES_M1 * nthr] = __float_as_uint(m[1]); es[ES_M2 * nthr] = __float_as_uint(m[2]);
+        es[ES_SCAN * nthr] = A.scan_first; es[ES_SEG * nthr] = SEG_START;
+        es[ES_EV * nthr] = 0u; es[ES_TSTOP * nthr] = 0u; es[ES_TOLD * nthr] = 0u; es[ES_RF * nthr] = 1u; es[ES_TE * nthr] = 0u;
+        es[ES_DEPH * nthr] = 0u; es[ES_GFIRST * nthr] = 0u; es[ES_RUNLEN * nthr] = 0u;
     }
-    // ---- resuming a long run after a re-binning pause (engine.cu: run_impl): position, magnetisation, substrate and RNG
-    //      block counter come back from the state arrays; everything else of the per-TR state is reset at a TR start anyway ----
-    uint32_t blk = 0;
-    const size_t st_idx = (size_t)k * A.n_local + jl;
-    if (A.scan_first > 0 && alive) {
-        const uint4 sa = A.state_a[st_idx], sb = A.state_b[st_idx];
-        p0 = sa.x; p1 = sa.y; p2 = sa.z; blk = sa.w;
-        m[0] = __uint_as_float(sb.x); m[1] = __uint_as_float(sb.y); m[2] = __uint_as_float(sb.z);
+    // current voxel: table index, substrate, field.  The reference loads field / T1 / T2 at the first accepted step
+    // (kernels.cu:91,150-170); holding the field of the CURRENT voxel from the start is equivalent: a first step that stays in
+    // the voxel reads this very value.
+    uint32_t idx_cur = VOX == VOX_SLAB ? (p0 >> fb) * n1 + (p1 >> fb) : ((p0 >> fb) * n1 + (p1 >> fb)) * n2 + (p2 >> fb);
+    uint32_t ind3_cur = ((p0 >> fb) * n1 + (p1 >> fb)) * n2 + (p2 >> fb); // STATS only
+    uint32_t wcur = 0;   // PACKED / SLAB: the packed word; MASK / SPLIT: the substrate id
+    float fcur = 0.f;    // SPLIT: field of the current voxel (Tesla)
+    if (valid) {
+        if (VOX == VOX_PACKED || VOX == VOX_SLAB) wcur = __ldg(A.packed + idx_cur);
+        else {
+            wcur = __ldg(A.mask + idx_cur);
+            if (VOX == VOX_SPLIT) fcur = __ldg(A.fieldmap + idx_cur);
+        }
+        if (A.scan_first > 0) { // the substrate a walker is IN (it equals its voxel's today: a rejected step is never taken)
+            if (VOX == VOX_PACKED || VOX == VOX_SLAB) wcur = (wcur & ~15u) | ts_saved; else wcur = ts_saved;
+        }
     }
-    const uint32_t ny = A.ny, nz = A.nz;
-    uint32_t ind_cur = ((p0 >> fb) * ny + (p1 >> fb)) * nz + (p2 >> fb);
-    uint32_t ts_old = alive ? (uint32_t)__ldg(A.mask + ind_cur) : 0u;
-    if (A.scan_first > 0 && alive) {
-        const uint32_t meta = A.state_b[st_idx].w; // substrate | lost << 8
-        ts_old = meta & 0xffu;
-        if (meta & 0x100u) alive = false; // lost in an earlier launch (already counted there)
-    }
-    const bool has_field = VOX != VOX_MASK;
-    const float field_k = A.field_k;
-    // The reference loads field / T1 / T2 at the first accepted step (kernels.cu:91,150-170).  Holding the field of
-    // the CURRENT voxel from the start is equivalent: a first step that stays in the voxel reads this very value.
-    float field = 0.f;
-    if (alive && VOX == VOX_SPLIT) field = __fmul_rn(__ldg(A.fieldmap + ind_cur), field_k);
-    if (alive && VOX == VOX_PACKED) field = __fmul_rn(__uint_as_float(__ldg(A.packed + ind_cur) & 0xfffffff0u), field_k);
-    if (alive && VOX == VOX_SLAB) field = __fmul_rn(__uint_as_float(__ldg(A.packed + ((p0 >> fb) * ny + (p1 >> fb))) & 0xfffffff0u), field_k);
-    float sg0 = sgt[3 * ts_old], sg1 = sgt[3 * ts_old + 1], sg2 = sgt[3 * ts_old + 2];
+    auto ts_of = [](uint32_t w) -> uint32_t { return (VOX == VOX_PACKED || VOX == VOX_SLAB) ? (w & 15u) : w; };
+    float sg0 = sgt[3 * ts_of(wcur)], sg1 = sgt[3 * ts_of(wcur) + 1], sg2 = sgt[3 * ts_of(wcur) + 2];
 
-    uint32_t itr = 0;
+    const size_t out_row = (size_t)kc * A.n_local + jl;
+    uint4 *stage = A.stage ? A.stage + out_row * A.stage_row : nullptr;            // [n_te] echoes (Mx, My, Mz, T) + final position
+    float *X1 = (RECORD && A.XYZ1) ? A.XYZ1 + out_row * A.trj * 3 : nullptr;       // trajectories go straight to the reference layout
+    if (RECORD && X1 && valid && A.scan_first == 0) { // slot 0 starts as the (scaled) initial position (kernels.cu:96)
+#pragma unroll
+        for (int i = 0; i < 3; i++) X1[i] = __fmul_rn(__ldg(A.xyz0 + 3 * (size_t)jl + i), SC.fscale);
+    }
+
+    // ---- registers of the round loop ----
+    float acc = 0.f;      // phase accrued since the last event (degrees)
+    int rem = 0;          // accepted steps still to take in the current segment
+    uint32_t itr = 0;     // consecutive rejections (kernels.cu:155)
+    uint32_t cnt_grad = 0;
+    bool grun = false;    // the current segment is a run of gradient samples (one per accepted step)
+    bool done = !valid;
+    bool fresh = true;    // STATS only (ind_old = matrix_length+1 at a TR start, kernels.cu:123)
+    uint32_t st_mask = 0, st_field = 0, st_rej = 0, st_steps = 0; // per thread and launch: < 2^32
+    const uint32_t n_tp = A.n_tp;
     const uint32_t seed_lo = (uint32_t)A.seed;
     const uint32_t seed_hi_walk = ((uint32_t)(A.seed >> 32) & 0x3fffffffu) | (STREAM_WALK << 30);
-    uint32_t st_mask = 0, st_field = 0, st_rej = 0, st_steps = 0; // per thread and launch: < 2^32
-    bool lost = false;
-
-    const size_t out_row = (size_t)k * A.n_local + jl;
-    float *M1 = A.M1 ? A.M1 + out_row * A.n_te * 3 : nullptr;
-    uint8_t *Tt = A.T ? A.T + out_row * A.n_te : nullptr;
-    float *X1 = A.XYZ1 ? A.XYZ1 + out_row * A.trj * 3 : nullptr;
-    if (RECORD && X1 && alive) { // slot 0 starts as the (scaled) initial position (kernels.cu:96)
-#pragma unroll
-        for (int i = 0; i < 3; i++) X1[i] = __fmul_rn(__ldg(A.xyz0 + 3 * (size_t)jl + i), fscale);
-    }
-
-    const uint32_t n_tp = A.n_tp;
-    // One Philox block feeds TWO attempts: the even attempt of block `blk` steps by (na*), the odd one by (nb*).
     const uint32_t kOne = A.one_bits; // 0x3f800000, deliberately opaque to ptxas (see and_or)
-    float na0, na1, na2, nb0, nb1, nb2;
-    normals6_fast(philox_fixed(blk, seed_lo, spin_no, seed_hi_walk), kOne, na0, na1, na2, nb0, nb1, nb2);
 
-    for (uint32_t scan = A.scan_first; scan < A.scan_end; scan++) {
-        const bool last_scan = (scan + 1 == A.n_scans);
-        { // phase cycling + first RF (kernels.cu:110-120)
-            float ph = (float)((double)(A.rf_ph0 + (float)scan * lin_pc) + (double)(scan * (scan + 1u)) / 2.0 * (double)A.quad_pc);
-            while (ph > 360.0) ph = (float)(ph - 360.0);
-            while (ph < 0) ph = (float)(ph + 360.0);
-            float r[3];
-            xrot_withphase(A.s, A.c, ph, m, r);
-            m[0] = r[0]; m[1] = r[1]; m[2] = r[2];
+    // ======================================= one attempt =======================================
+    // one tentative step (kernels.cu:130-170) with the normals of round `r`; `perm_u` yields the permeability uniform of the round.
+    auto attempt = [&](const float a0, const float a1, const float a2, const uint32_t r, auto &&perm_u) {
+        const bool act = rem > 0;
+        uint32_t q0 = fx_step(p0, a0, sg0), q1 = fx_step(p1, a1, sg1), q2 = fx_step(p2, a2, sg2);
+        uint32_t v0 = q0 >> fb, v1 = q1 >> fb, v2 = q2 >> fb;
+        if (act & ((v0 >= n0) | (v1 >= n1) | (v2 >= n2))) { // FoV boundary (kernels.cu:133-136), rare
+            if (v0 >= n0) { q0 = fov_boundary(q0, p0, n0, fb, A.cross_fov); v0 = q0 >> fb; }
+            if (v1 >= n1) { q1 = fov_boundary(q1, p1, n1, fb, A.cross_fov); v1 = q1 >> fb; }
+            if (v2 >= n2) { q2 = fov_boundary(q2, p2, n2, fb, A.cross_fov); v2 = q2 >> fb; }
         }
-        uint32_t t = 0, t_old = 0;
-        uint32_t cur_rf = 1, cur_te = 0, cnt_deph = 0, cnt_grad = 0;
-        float acc = 0.f;
-        bool fresh = true; // only for the STATS counters (ind_old = matrix_length+1, kernels.cu:123)
-
-        // The timeline is walked entry by entry: steps up to and including the entry's timepoint, then its events.  A RUN of
-        // gradient-only samples at consecutive timepoints (a PGSE lobe: one sample per step for 10 ms) is taken in one go
-        // instead: the plain steps before its first timepoint (part 0), then one step + one gradient sample per timepoint inside
-        // the inner loop itself (part 1) — no segment restart per sample.
-        for (uint32_t ev = 0; ev <= L.n_tl;) {
-            const uint32_t ev_time = ev < L.n_tl ? (uint32_t)tl_time[ev] : n_tp;
-            const uint32_t run = ev < L.n_tl ? tl_run[ev] : 0u;
-            const bool is_run = GRUNS && run >= 2u && ev_time < n_tp;
-            const uint32_t run_len = is_run ? min(run, n_tp - ev_time) : 0u;
-          for (int part = 0; part < (is_run ? 2 : 1); part++) {
-            const bool grun = GRUNS && part == 1;
-            const uint32_t t_stop = is_run ? (grun ? ev_time + run_len : ev_time) : (ev_time < n_tp ? ev_time + 1u : n_tp);
-            const uint32_t grad_first = cnt_grad;
-            int rem = alive ? (int)(t_stop - t) : 0; // accepted steps still to take in this part
-
-            // =============================== inner loop ===============================
-            // one attempt = one tentative step (kernels.cu:130-170).  `overlap` is independent work (random numbers of later
-            // attempts) placed between ISSUING the voxel gather and CONSUMING it.  Returns true when the step was accepted.
-            auto attempt = [&](const float a0, const float a1, const float a2, const uint32_t perm_ctr, auto &&overlap) -> bool {
-                uint32_t q0 = fx_step(p0, a0, sg0), q1 = fx_step(p1, a1, sg1), q2 = fx_step(p2, a2, sg2);
-                const bool hop = (((p0 ^ q0) | (p1 ^ q1) | (p2 ^ q2)) >> fb) != 0u;
-                uint32_t ts = ts_old;
-                float fv = 0.f;
-                uint32_t ind_new = ind_cur; // STATS bookkeeping only
-                bool chg = false;
-                if (hop) {
-                    uint32_t v0 = q0 >> fb, v1 = q1 >> fb, v2 = q2 >> fb;
-                    if ((v0 >= n3[0]) | (v1 >= n3[1]) | (v2 >= n3[2])) { // FoV boundary (kernels.cu:133-136), rare
-                        if (v0 >= n3[0]) { q0 = fov_boundary(q0, p0, n3[0], fb, A.cross_fov); v0 = q0 >> fb; }
-                        if (v1 >= n3[1]) { q1 = fov_boundary(q1, p1, n3[1], fb, A.cross_fov); v1 = q1 >> fb; }
-                        if (v2 >= n3[2]) { q2 = fov_boundary(q2, p2, n3[2], fb, A.cross_fov); v2 = q2 >> fb; }
-                    }
-                    ind_new = (v0 * ny + v1) * nz + v2;
-                    if (STATS) { chg = (ind_new != ind_cur) | fresh; st_mask += chg; }
-                    if (VOX == VOX_PACKED || VOX == VOX_SLAB) { // one gather
-                        const uint32_t w = ldg_voxel(A.packed + (VOX == VOX_SLAB ? v0 * ny + v1 : ind_new));
-                        ts = w & 15u;
-                        fv = __uint_as_float(w & 0xfffffff0u);
-                    } else {                 // both gathers issued back to back
-                        ts = __ldg(A.mask + ind_new);
-                        if (VOX == VOX_SPLIT) fv = __ldg(A.fieldmap + ind_new);
-                    }
-                } else if (STATS && fresh) {
-                    st_mask++; st_field++;
-                }
-                overlap();
-                if (hop) { // kernels.cu:150-170
-                    if (ts != ts_old) {
-                        // accept iff u < P_XY[from][to], u in [0,1) (kernels.cu:154).  P <= 0 always rejects and P >= 1 always accepts:
-                        // the uniform (its own Philox2x32 stream, so skipping a draw changes nothing else) is only generated in between.
-                        const float pxy = tpXY[ts_old * L.n_sub + ts];
-                        bool reject = pxy <= 0.f;
-                        if (pxy > 0.f && pxy < 1.f) reject = u01_open1(philox2x32_10(perm_ctr, spin_no, A.perm_key)) >= pxy;
-                        if (reject) {
-                            if (STATS) st_rej++;
-                            if (itr++ > A.max_iter) { alive = false; lost = true; rem = 0; }
-                            return false; // redraw from the old position; time does not advance
-                        }
-                        ts_old = ts;
-                        sg0 = sgt[3 * ts]; sg1 = sgt[3 * ts + 1]; sg2 = sgt[3 * ts + 2];
-                    }
-                    if (has_field) field = __fmul_rn(fv, field_k); // monte_carlo.cu:244
-                    if (STATS) { st_field += chg; ind_cur = ind_new; }
-                }
-                if (STATS) { fresh = false; st_steps++; }
-                p0 = q0; p1 = q1; p2 = q2;
-                acc += field; // kernels.cu:171-172
-                itr = 0;
-                if (GRUNS && grun) { // gradient sample of this timepoint, at the NEW position (kernels.cu:181-187); FP32 here, FP64 in the event path
-                    const float gx = __fmul_rn(gtx[cnt_grad], gscale), gy = __fmul_rn(gty[cnt_grad], gscale), gz = __fmul_rn(gtz[cnt_grad], gscale);
-                    acc += gx * ((float)p0 * umk[0]) + gy * ((float)p1 * umk[1]) + gz * ((float)p2 * umk[2]);
-                    cnt_grad++;
-                }
-                if (RECORD) { // kernels.cu:218-221 (diagnostic mode)
-                    if (X1) {
-                        float *slot = X1 + 3 * ((size_t)scan * n_tp + (t_stop - (uint32_t)rem));
-                        slot[0] = (float)((double)p0 * unit_m[0]); slot[1] = (float)((double)p1 * unit_m[1]); slot[2] = (float)((double)p2 * unit_m[2]);
-                    }
-                }
-                return true;
-            };
-            // The integer half of the next block (Philox rounds) overlaps the gather of the even attempt, the float half
-            // (Box-Muller) that of the odd attempt.  A segment always starts on a fresh block (lanes of a warp stay in phase).
-            while (rem > 0) {
-                uint4 raw;
-                if (attempt(na0, na1, na2, 2u * blk, [&] { raw = philox_fixed(blk + 1u, seed_lo, spin_no, seed_hi_walk); })) rem--;
-                if (rem <= 0) { // the segment ends on an even attempt: (nb*) of this block are dropped
-                    normals6_fast(raw, kOne, na0, na1, na2, nb0, nb1, nb2);
-                    blk++;
-                    break;
-                }
-                if (attempt(nb0, nb1, nb2, 2u * blk + 1u, [&] { normals6_fast(raw, kOne, na0, na1, na2, nb0, nb1, nb2); })) rem--;
-                blk++;
+        const uint32_t idx = VOX == VOX_SLAB ? v0 * n1 + v1 : (v0 * n1 + v1) * n2 + v2;
+        uint32_t w = wcur;
+        float fv = fcur;
+        if (act & (idx != idx_cur)) { // the voxel changed: one gather
+            if (VOX == VOX_PACKED || VOX == VOX_SLAB) w = ldg_voxel(A.packed + idx);
+            else {
+                w = __ldg(A.mask + idx);
+                if (VOX == VOX_SPLIT) fv = __ldg(A.fieldmap + idx);
             }
-            t = t_stop - (uint32_t)rem;
-            if (grun) cnt_grad = grad_first + run_len; // also for lanes that are no longer alive
-          }
-            // ============================ end of inner loop ============================
-            if (is_run) { ev += run_len; continue; } // (a run clipped by the end of the TR is followed by entries >= n_tp only)
-            if (ev >= L.n_tl) break;
-            if (ev_time >= n_tp) break;
-
-            // ---- events of timepoint ev_time, in the reference's order (kernels.cu:175-215) ----
-            const uint32_t mask_ev = tl_mask[ev];
-            const uint32_t tp = ev_time;
-            if (mask_ev & EV_DEPH) { // kernels.cu:175-178
-                if (alive) acc += (float)spin_no * blob_ptr<float>(B, L.deph_deg)[cnt_deph] / (float)A.n_spins_global;
-                cnt_deph++;
+        }
+        bool chg = false;
+        uint32_t ind3 = 0;
+        if (STATS) {
+            ind3 = (v0 * n1 + v1) * n2 + v2;
+            chg = act & ((ind3 != ind3_cur) | fresh);
+            st_mask += chg;
+        }
+        bool ok = act;
+        if ((VOX == VOX_PACKED || VOX == VOX_SLAB) ? (((w ^ wcur) & 15u) != 0u) : (w != wcur)) { // kernels.cu:150-164 (only a lane that hopped gets here)
+            // accept iff u < P_XY[from][to], u in [0,1) (kernels.cu:154).  P <= 0 always rejects and P >= 1 always accepts.
+            const float pxy = tpXY[ts_of(wcur) * L.n_sub + ts_of(w)];
+            bool reject = pxy <= 0.f;
+            if (pxy > 0.f && pxy < 1.f) reject = perm_u(r) >= pxy;
+            if (reject) {
+                ok = false;
+                if (STATS) st_rej++;
+                if (itr++ > A.max_iter) { lost = true; rem = 0; } // kernels.cu:155-159
+            } else {
+                sg0 = sgt[3 * ts_of(w)]; sg1 = sgt[3 * ts_of(w) + 1]; sg2 = sgt[3 * ts_of(w) + 2];
             }
-            if (mask_ev & EV_GRAD) { // kernels.cu:181-187
-                if (alive) {
-                    const float Gx = __fmul_rn(blob_ptr<float>(B, L.gx)[cnt_grad], gscale), Gy = __fmul_rn(blob_ptr<float>(B, L.gy)[cnt_grad], gscale),
-                                Gz = __fmul_rn(blob_ptr<float>(B, L.gz)[cnt_grad], gscale); // monte_carlo.cu:288-290
-                    const double X = (double)p0 * unit_m[0], Y = (double)p1 * unit_m[1], Z = (double)p2 * unit_m[2];
-                    double g = __fma_rn((double)Gz, Z, __fma_rn((double)Gx, X, __dmul_rn((double)Gy, Y)));
-                    g = g * 1e-3 * (double)A.timestep_us * 1e-6 * kGamma;
-                    acc = (float)__fma_rn(g, kRad2Deg, (double)acc);
-                }
+        }
+        if (ok) { // commit (kernels.cu:165-172, 218-223)
+            p0 = q0; p1 = q1; p2 = q2;
+            idx_cur = idx;
+            wcur = w;
+            fcur = fv;
+            if (VOX == VOX_PACKED || VOX == VOX_SLAB) acc = fmaf(__uint_as_float(w), A.field_k, acc); // kernels.cu:171-172, monte_carlo.cu:244
+            else if (VOX == VOX_SPLIT) acc = fmaf(fv, A.field_k, acc);
+            itr = 0;
+            rem--;
+            if (STATS) { st_field += chg; ind3_cur = ind3; fresh = false; st_steps++; }
+            if (GRUNS && grun) { // gradient sample of this timepoint, at the NEW position (kernels.cu:181-187); FP32 here, FP64 in the event path
+                const float gs = SC.gscale;
+                const float gx = __fmul_rn(gtx[cnt_grad], gs), gy = __fmul_rn(gty[cnt_grad], gs), gz = __fmul_rn(gtz[cnt_grad], gs);
+                acc += gx * ((float)p0 * SC.umk[0]) + gy * ((float)p1 * SC.umk[1]) + gz * ((float)p2 * SC.umk[2]);
                 cnt_grad++;
             }
-            if (mask_ev & EV_RF) { // kernels.cu:190-199
-                if (alive) {
-                    const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
-                    dephase_relax(m, acc, tT1[ts_old], tT2[ts_old], dt_s);
-                    float r[3];
-                    xrot_withphase(blob_ptr<float>(B, L.rf_s)[cur_rf], blob_ptr<float>(B, L.rf_c)[cur_rf], blob_ptr<float>(B, L.rf_ph)[cur_rf], m, r);
-                    m[0] = r[0]; m[1] = r[1]; m[2] = r[2];
-                    acc = 0.f;
-                    t_old = tp;
-                }
-                cur_rf++;
+            if (RECORD && X1) { // kernels.cu:218-221 (diagnostic mode)
+                float *slot = X1 + 3 * ((size_t)es[ES_SCAN * nthr] * n_tp + (es[ES_TSTOP * nthr] - 1u - (uint32_t)rem));
+                slot[0] = (float)((double)p0 * SC.unit_m[0]); slot[1] = (float)((double)p1 * SC.unit_m[1]); slot[2] = (float)((double)p2 * SC.unit_m[2]);
             }
-            if ((mask_ev & EV_ECHO) && last_scan) { // kernels.cu:202-215
-                if (alive) {
-                    const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
-                    dephase_relax(m, acc, tT1[ts_old], tT2[ts_old], dt_s);
-                    if (M1) { M1[3 * cur_te + 0] = m[0]; M1[3 * cur_te + 1] = m[1]; M1[3 * cur_te + 2] = m[2]; }
-                    if (Tt) Tt[cur_te] = (uint8_t)ts_old;
-                    acc = 0.f;
-                    t_old = tp;
-                }
-                if (A.sums) { // ensemble sums per substrate: warp shuffle, then shared-memory accumulate
-                    const uint32_t lane = threadIdx.x & 31u;
-                    for (uint32_t sub = 0; sub < L.n_sub; sub++) {
-                        const bool mine = alive && ts_old == sub;
-                        const unsigned any = __ballot_sync(0xffffffffu, mine);
-                        if (!any) continue;
-                        const float sx = warp_sum(mine ? m[0] : 0.f), sy = warp_sum(mine ? m[1] : 0.f), sz = warp_sum(mine ? m[2] : 0.f);
-                        if (lane == 0) {
-                            float *b = bsum + (cur_te * L.n_sub + sub) * 4u;
-                            atomicAdd(b + 0, sx); atomicAdd(b + 1, sy); atomicAdd(b + 2, sz);
-                            atomicAdd(b + 3, (float)__popc(any));
-                        }
-                    }
-                }
-                cur_te++;
-            }
-            ev++;
         }
-        if (alive) { // end of TR (kernels.cu:226-231)
-            const float dt_s = (float)((double)((n_tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
-            dephase_relax(m, acc, tT1[ts_old], tT2[ts_old], dt_s);
-        }
-    }
+    };
 
-    // ---- final position (kernels.cu:220-221 leaves the last committed position in xyz1) ----
-    if (A.scan_end < A.n_scans) { // pause at a TR boundary: (na*, nb*) are the untouched normals of block `blk`, so the counter is the whole RNG state
-        if (j < A.j_end) {
-            A.state_a[st_idx] = make_uint4(p0, p1, p2, blk);
-            A.state_b[st_idx] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts_old | ((alive ? 0u : 1u) << 8));
-            A.state_vox[st_idx] = ((p0 >> fb) * ny + (p1 >> fb)) * nz + (p2 >> fb);
+    // ======================================= events =======================================
+    AdvCtx cx;
+    cx.A = &A; cx.B = B; cx.SC = &SC; cx.es = es; cx.bsum = bsum + (size_t)k_loc * n_bsum; cx.stage = stage; cx.st_idx = st_idx;
+    cx.spin_no = spin_no; cx.nthr = nthr; cx.n_bsum = n_bsum;
+    auto advance = [&](const uint32_t r_next) { // (see advance_walker)
+        const AdvOut o = advance_walker<STATS, RECORD, VOX, GRUNS>(&cx, p0, p1, p2, wcur, acc, cnt_grad,
+                                                                  (lost ? WF_LOST : 0u) | (grun ? WF_GRUN : 0u) | (fresh ? WF_FRESH : 0u), r_next);
+        acc = o.acc; rem = o.rem; cnt_grad = o.cnt_grad;
+        done = (o.flags & WF_DONE) != 0u; grun = (o.flags & WF_GRUN) != 0u;
+        if (STATS) fresh = (o.flags & WF_FRESH) != 0u;
+    };
+
+    if (!done) advance(r_first); // start of the first TR of this launch
+
+    if (SHARED) {
+        auto generate = [&](float4 *buf, const uint32_t r0) {
+            generate_normals(buf, r0, spin_no, seed_lo, seed_hi_walk, kOne, A.perm_draws ? A.perm_key : nullptr);
+        };
+        uint32_t r0 = 0, cur = 0;
+        generate(nbuf, 0u);
+        for (;;) {
+            if (!__syncthreads_or(!done)) break; // also: batch `cur` is visible, and everybody has finished reading the other buffer
+            generate(nbuf + (cur ^ 1u) * (kBatch * 32u), r0 + kBatch);
+            if (!done) {
+#pragma unroll 1
+                for (uint32_t h = 0; h < kBatch; h += kSync) {
+                    const float4 *nb = nbuf + cur * (kBatch * 32u) + h * 32u + lane;
+                    float4 n = nb[0];
+#pragma unroll
+                    for (uint32_t rr = 0; rr < kSync; rr++) {
+                        const float4 c = n;
+                        if (rr + 1u < kSync) n = nb[(rr + 1u) * 32u]; // the next round's normals are in flight while this one is taken
+                        attempt(c.x, c.y, c.z, r0 + h + rr, [&](uint32_t) { return c.w; });
+                    }
+                    if (rem == 0) advance(r0 + h + kSync);
+                    if (done) break;
+                }
+            }
+            r0 += kBatch;
+            cur ^= 1u;
         }
-    }
-    if (!RECORD && X1 && j < A.j_end && A.scan_end == A.n_scans) {
-        X1[0] = (float)((double)p0 * unit_m[0]); X1[1] = (float)((double)p1 * unit_m[1]); X1[2] = (float)((double)p2 * unit_m[2]);
+    } else {
+        uint32_t r = r_first;
+        while (!done) {
+#pragma unroll 1
+            for (uint32_t h = 0; h < kSync; h += 2u) {
+                float a0, a1, a2, b0, b1, b2;
+                normals6_fast(philox_fixed(r >> 1, seed_lo, spin_no, seed_hi_walk), kOne, a0, a1, a2, b0, b1, b2);
+                auto pu = [&](uint32_t rr) { return u01_open1(philox2x32_10(rr, spin_no, A.perm_key)); };
+                attempt(a0, a1, a2, r, pu);
+                attempt(b0, b1, b2, r + 1u, pu);
+                r += 2u;
+            }
+            if (rem == 0) advance(r);
+        }
     }
 
     // ---- flush block sums and counters ----
     __syncthreads();
-    if (A.sums) {
-        double *gs = A.sums + (size_t)k * n_bsum;
-        for (uint32_t i = threadIdx.x; i < n_bsum; i += kBlock) {
-            const float v = bsum[i];
-            if (v != 0.f) atomicAdd(gs + i, (double)v);
+    if (A.sums_fx) {
+        for (uint32_t i = threadIdx.x; i < n_bsum * n_grp; i += nthr) {
+            const uint32_t kk = k_first + i / n_bsum;
+            const long long v = bsum[i];
+            if (v != 0 && kk < A.n_scales) atomicAdd(A.sums_fx + (size_t)kk * n_bsum + (i % n_bsum), (unsigned long long)v);
         }
     }
     if (A.counters) {
@@ -508,15 +632,15 @@ __global__ void __launch_bounds__(kBlock, SWK_FAST_MIN_BLOCKS) walk_fast_kernel(
                 c2 += __shfl_xor_sync(0xffffffffu, c2, o);
                 c3 += __shfl_xor_sync(0xffffffffu, c3, o);
             }
-            if ((threadIdx.x & 31u) == 0) {
+            if (lane == 0) {
                 atomicAdd(A.counters + 0, c0);
                 atomicAdd(A.counters + 1, c1);
                 atomicAdd(A.counters + 2, c2);
                 atomicAdd(A.counters + 3, c3);
             }
         }
-        const unsigned lost_w = __popc(__ballot_sync(0xffffffffu, lost));
-        if ((threadIdx.x & 31u) == 0 && lost_w) atomicAdd(A.counters + 4, (unsigned long long)lost_w);
+        const unsigned lost_w = __popc(__ballot_sync(0xffffffffu, lost && !lost_before)); // spins abandoned in THIS launch
+        if (lane == 0 && lost_w) atomicAdd(A.counters + 4, (unsigned long long)lost_w);
     }
 }
 

@@ -16,10 +16,9 @@
 //   * per-(scale, echo, substrate) ensemble sums are reduced in-kernel (warp shuffle -> shared -> one
 //     FP64 global atomic per block), which the reference leaves to post-processing.
 //
-// Two arithmetic modes (include/spinwalk_engine.h):
-//   SWK_MODE_COMPAT: minstd_rand + erfcinvf normal + FP64 metres — reproduces the reference CUDA
-//                    build's walk bit for bit (same device, same libdevice erfcinvf).
-//   SWK_MODE_FAST:   Philox4x32-10 + Box-Muller + (voxel, fraction) FP32 grid coordinates.
+// This file holds the shared types / helpers and the SWK_MODE_COMPAT kernel: minstd_rand + erfcinvf normal +
+// FP64 metres — the reference CUDA build's walk bit for bit (same device, same libdevice erfcinvf).
+// SWK_MODE_FAST (the product path) is walk_fast.cuh; it shares nothing with this kernel but the helpers.
 #pragma once
 
 #include <cstdint>
@@ -83,11 +82,19 @@ struct WalkArgs {
     uint4   *state_a, *state_b;    // [n_scales][n_local]: (p0, p1, p2, RNG block counter), (Mx, My, Mz, substrate | lost << 8)
     uint32_t *state_vox;           // [n_scales][n_local]: linear voxel index at the pause (sort key of the next launch)
     uint32_t j_first, j_end; // this launch simulates thread slots [j_first, j_end) of the shard (pipelined host runs launch slices)
-    // outputs (any may be nullptr), reference layouts restricted to the shard
-    float   *M1;             // [K][n_local][E][3]
-    float   *XYZ1;           // [K][n_local][trj][3]
-    uint8_t *T;              // [K][n_local][E]
-    double  *sums;           // [K][E][n_sub][4]
+    // FAST mode: per-scale constants (walk_fast.cuh ScaleConst + sigma table), and how blocks are cut
+    const uint8_t *scale_tab;
+    uint32_t scale_stride;   // bytes per scale record (multiple of 16)
+    uint32_t group, n_groups; // SHARED variant: scales per block (block = 32 x group threads), groups per spin chunk
+    int32_t  perm_draws;     // some 0 < P_XY < 1: permeability uniforms are needed
+    // outputs (any may be nullptr)
+    // Per-spin results go to STAGING ROWS, one per (scale, local spin): n_te echo slots (Mx, My, Mz, tissue) and one slot for the final
+    // position, 16 bytes each — a thread's scattered result write is whole aligned 16/32-byte pieces instead of three partial-sector
+    // stores into three arrays; unpack_rows_kernel (engine.cu) streams the rows into the reference layouts below.
+    uint4   *stage;          // [K][n_local][stage_row]
+    uint32_t stage_row;      // n_te + 1
+    float   *XYZ1;           // [K][n_local][trj][3]: written directly only when trajectories are recorded
+    unsigned long long *sums_fx; // [K][E][n_sub][4]: sum Mx, My, Mz in fixed point (kSumScale), count
     unsigned long long *counters; // [5]: steps, mask_gathers, field_gathers, rejects, lost
     uint64_t trj;
 };
@@ -193,10 +200,8 @@ __device__ __forceinline__ float minstd_uniform(uint32_t &x)
 }
 
 // ------------------------------------------------------------------------------------------------
-// RNG, fast flavour: Philox4x32-10 (Salmon et al., SC'11), counter-based.
-//   key     = (seed lo, seed hi)
-//   counter = (attempt counter, 0, global spin id, stream tag)
-// The same stream is used for every scale, like the reference re-seeding seed+spin per scale.
+// Philox4x32-10 (Salmon et al., SC'11) with a (seed lo, seed hi) key: the device-side default start
+// positions (init_positions_kernel below).  The FAST walk's own generators live in walk_fast.cuh.
 // ------------------------------------------------------------------------------------------------
 enum : uint32_t { STREAM_WALK = 0u, STREAM_PERMEABILITY = 1u, STREAM_XYZ0 = 2u };
 
@@ -221,19 +226,6 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ float u01_open0(uint32_t r) { return 2.0f - __uint_as_float((r >> 9) | 0x3f800000u); }
 __device__ __forceinline__ float u01_open1(uint32_t r) { return __uint_as_float((r >> 9) | 0x3f800000u) - 1.0f; }
 
-// three standard normals from one Philox block (Box-Muller; hardware lg2/sqrt/sin/cos)
-__device__ __forceinline__ void normals3(const uint4 r, float &n0, float &n1, float &n2)
-{
-    const float kNeg2Ln2 = -1.3862943611198906f, k2Pi = 6.283185307179586f;
-    float ra = sqrtf(kNeg2Ln2 * __log2f(u01_open0(r.x)));
-    float rb = sqrtf(kNeg2Ln2 * __log2f(u01_open0(r.z)));
-    float sa, ca;
-    __sincosf(k2Pi * u01_open1(r.y), &sa, &ca);
-    n0 = ra * ca;
-    n1 = ra * sa;
-    n2 = rb * __cosf(k2Pi * u01_open1(r.w));
-}
-
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -242,16 +234,36 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// Ensemble sums in integer fixed point: a component is rounded to a multiple of 2^-22 once, every addition after that is exact, so the
+// sums are order independent and bit-reproducible run to run (and across shards).  |M| < 16 is assumed (|M| <= 1 for M0 = (0,0,1)).
+// May be called from divergent code: the lanes of a warp that arrive together with the same key (echo, substrate) are found with
+// match.any and reduced with the warp's integer reduction unit; one lane per group adds to the block's shared-memory accumulators.
+constexpr float kSumScale = 4194304.f; // 2^22
+__device__ __forceinline__ void echo_sums_add(long long *b /* [entries][4] */, uint32_t key, const float *m)
+{
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    const int sx = __reduce_add_sync(peers, __float2int_rn(m[0] * kSumScale));
+    const int sy = __reduce_add_sync(peers, __float2int_rn(m[1] * kSumScale));
+    const int sz = __reduce_add_sync(peers, __float2int_rn(m[2] * kSumScale));
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) {
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(b) + (size_t)key * 4u;
+        atomicAdd(d + 0, (unsigned long long)(long long)sx);
+        atomicAdd(d + 1, (unsigned long long)(long long)sy);
+        atomicAdd(d + 2, (unsigned long long)(long long)sz);
+        atomicAdd(d + 3, (unsigned long long)__popc(peers));
+    }
+}
+
 template <class T>
 __device__ __forceinline__ const T *blob_ptr(const uint8_t *base, uint32_t off) { return reinterpret_cast<const T *>(base + off); }
 
 // ------------------------------------------------------------------------------------------------
-// The kernel.  One thread = one (spin, scale).  grid = ceil(n_local/256) * n_scales blocks; consecutive
+// The COMPAT kernel.  One thread = one (spin, scale).  grid = ceil(n_local/256) * n_scales blocks; consecutive
 // blocks take consecutive SCALES of the same spin chunk so that memory-bound (small FoV scale) and
 // issue-bound (large FoV scale) blocks share an SM.
 // ------------------------------------------------------------------------------------------------
-template <int MODE, bool STATS>
-__global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock) walk_compat_kernel(const WalkArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlobLayout &L = A.L;
@@ -267,10 +279,10 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
         B = smem;
         smem_used = L.bytes;
     }
-    // block-level sums [E][n_sub][4] (float) after the tables
-    float *bsum = reinterpret_cast<float *>(smem + smem_used);
-    const uint32_t n_bsum = A.sums ? A.n_te * L.n_sub * 4u : 0u;
-    for (uint32_t i = threadIdx.x; i < n_bsum; i += kBlock) bsum[i] = 0.f;
+    // block-level sums [E][n_sub][4] (int64 fixed point) after the tables
+    long long *bsum = reinterpret_cast<long long *>(smem + smem_used);
+    const uint32_t n_bsum = A.sums_fx ? A.n_te * L.n_sub * 4u : 0u;
+    for (uint32_t i = threadIdx.x; i < n_bsum; i += kBlock) bsum[i] = 0;
     __syncthreads();
 
     const int32_t  *tl_time = blob_ptr<int32_t>(B, L.tl_time);
@@ -289,12 +301,11 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
     const uint32_t spin_no = A.spin_first + jl;                          // GLOBAL spin id
     const float scale = __ldg(A.scales + k);
 
-    float fscale = 1.f, gscale = 1.f, lin_pc = A.lin_pc;
-    if (A.scale_type == SWK_SCALE_FOV) fscale = scale;
-    else if (A.scale_type == SWK_SCALE_GRADIENT) gscale = scale;
+    float gscale = 1.f, lin_pc = A.lin_pc;
+    if (A.scale_type == SWK_SCALE_GRADIENT) gscale = scale;
     else if (A.scale_type == SWK_SCALE_PHASE_CYCLING) lin_pc = __fmul_rn(A.lin_pc, scale); // monte_carlo.cu:303
 
-    // ---- per-spin state -----------------------------------------------------------------------
+    // ---- per-spin state: FP64 metres (kernels.cu:93-99) -----------------------------------------
     float m[3] = {0.f, 0.f, 1.f};
     float x0[3] = {0.f, 0.f, 0.f};
     if (alive) {
@@ -305,21 +316,11 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
         }
     }
     const int64_t nyz = (int64_t)A.ny * A.nz;
-
-    // COMPAT state: FP64 metres (kernels.cu:93-99)
     double px[3] = {0, 0, 0}, fov_d[3] = {1, 1, 1}, s2g[3] = {0, 0, 0}, sigma_d = 0.;
     uint32_t rng_r = 1, rng_u = 1;
-    // FAST state: voxel + fraction, sigma in grid units
-    float pf[3] = {0, 0, 0}, sg[3] = {0, 0, 0};
-    int   pv[3] = {0, 0, 0};
-    float inv_h[3] = {0, 0, 0};
-    uint32_t ctr = 0;
-    const uint32_t key0 = (uint32_t)A.seed, key1 = (uint32_t)(A.seed >> 32);
-
     int64_t ind_cur = 0;
     uint32_t ts_old = 0;
-
-    if (MODE == SWK_MODE_COMPAT) {
+    {
         const uint32_t n3[3] = {A.nx, A.ny, A.nz};
 #pragma unroll
         for (int i = 0; i < 3; i++) {
@@ -337,45 +338,21 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
             sigma_d = tsigma[ts_old];
             rng_r = rng_u = minstd_init(A.seed + spin_no); // kernels.cu:77-88: identical streams
         }
-    } else {
-        const uint32_t n3[3] = {A.nx, A.ny, A.nz};
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            inv_h[i] = (float)n3[i] / A.fov[i]; // grid units per metre at scale 1
-            float g = x0[i] * inv_h[i];
-            float fl = floorf(g);
-            int v = (int)fl;
-            v = max(0, min(v, (int)n3[i] - 1));
-            pv[i] = v;
-            pf[i] = fminf(fmaxf(g - (float)v, 0.f), 0.99999994f);
-        }
-        ind_cur = (int64_t)pv[0] * nyz + (int64_t)pv[1] * A.nz + pv[2];
-        if (alive) {
-            ts_old = __ldg(A.mask + ind_cur);
-#pragma unroll
-            for (int i = 0; i < 3; i++) sg[i] = (float)(tsigma[ts_old] * (double)inv_h[i] / (double)fscale);
-        }
     }
 
     float field = 0.f, T1 = 0.f, T2 = 0.f; // kernels.cu:91
-    float xyz_f[3] = {0, 0, 0};            // last committed position as the reference stores it (float metres)
-    if (MODE == SWK_MODE_COMPAT) {
+    float xyz_f[3];                        // last committed position as the reference stores it (float metres)
 #pragma unroll
-        for (int i = 0; i < 3; i++) xyz_f[i] = (float)px[i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 3; i++) xyz_f[i] = __fmul_rn(x0[i], fscale);
-    }
+    for (int i = 0; i < 3; i++) xyz_f[i] = (float)px[i];
 
     unsigned long long st_mask = 0, st_field = 0, st_rej = 0, st_steps = 0;
     uint32_t itr = 0;
     bool lost = false;
 
     const size_t out_row = (size_t)k * A.n_local + jl;
-    float *M1 = A.M1 ? A.M1 + out_row * A.n_te * 3 : nullptr;
-    uint8_t *Tt = A.T ? A.T + out_row * A.n_te : nullptr;
-    float *X1 = A.XYZ1 ? A.XYZ1 + out_row * A.trj * 3 : nullptr;
-    if (A.record && X1 && alive) { // slot 0 starts as the (scaled) initial position (kernels.cu:96)
+    uint4 *stage = (A.stage && j < A.j_end) ? A.stage + out_row * A.stage_row : nullptr; // echo slots + final position (WalkArgs)
+    float *X1 = (A.record && A.XYZ1) ? A.XYZ1 + out_row * A.trj * 3 : nullptr;
+    if (X1 && alive) { // slot 0 starts as the (scaled) initial position (kernels.cu:96)
         X1[0] = xyz_f[0]; X1[1] = xyz_f[1]; X1[2] = xyz_f[2];
     }
 
@@ -384,6 +361,7 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
     const float field_k = A.field_k;
     const bool has_field = A.fieldmap != nullptr;
 
+    uint32_t echoes_done = 0; // echo events that fired in the last scan
     for (uint32_t scan = 0; scan < A.n_scans; scan++) {
         const bool last_scan = (scan + 1 == A.n_scans);
         // ---- phase cycling + first RF (kernels.cu:110-120) ----
@@ -407,94 +385,39 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
 
             // =============================== inner loop ===============================
             while (alive && t < t_stop) {
-                int64_t ind_new;
-                bool moved; // voxel index differs from the current one (or first step of a TR)
                 double nx_d[3];
-                float nf[3];
-                int nv[3];
-                if (MODE == SWK_MODE_COMPAT) {
-                    // kernels.cu:130-137
+                // kernels.cu:130-137
 #pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        nx_d[i] = px[i];
-                        if (sigma_d != 0.) {
-                            double rnd = __dmul_rn((double)minstd_normal(rng_r), sigma_d);
-                            double xn = __dadd_rn(px[i], rnd);
-                            if (xn < 0)
-                                xn = __dadd_rn(xn, A.cross_fov ? fov_d[i] : __dadd_rn(fabs(rnd), fabs(rnd)));
-                            else if (xn >= fov_d[i])
-                                xn = __dadd_rn(xn, -(A.cross_fov ? fov_d[i] : __dadd_rn(fabs(rnd), fabs(rnd))));
-                            nx_d[i] = xn;
-                        }
+                for (int i = 0; i < 3; i++) {
+                    nx_d[i] = px[i];
+                    if (sigma_d != 0.) {
+                        double rnd = __dmul_rn((double)minstd_normal(rng_r), sigma_d);
+                        double xn = __dadd_rn(px[i], rnd);
+                        if (xn < 0)
+                            xn = __dadd_rn(xn, A.cross_fov ? fov_d[i] : __dadd_rn(fabs(rnd), fabs(rnd)));
+                        else if (xn >= fov_d[i])
+                            xn = __dadd_rn(xn, -(A.cross_fov ? fov_d[i] : __dadd_rn(fabs(rnd), fabs(rnd))));
+                        nx_d[i] = xn;
                     }
-                    int64_t ix = (int64_t)__dmul_rn(nx_d[0], s2g[0]), iy = (int64_t)__dmul_rn(nx_d[1], s2g[1]),
-                            iz = (int64_t)__dmul_rn(nx_d[2], s2g[2]);
-                    ind_new = ix * nyz + iy * (int64_t)A.nz + iz; // kernels.cu:140
-                    if (ind_new >= A.V || ind_new < 0) {          // kernels.cu:141-147
-                        alive = false; lost = true;
-                        break;
-                    }
-                    moved = fresh || ind_new != ind_cur;
-                } else {
-                    const uint4 r = philox4x32_10(ctr, 0u, spin_no, STREAM_WALK, key0, key1);
-                    float d[3];
-                    normals3(r, d[0], d[1], d[2]);
-                    const int n3[3] = {(int)A.nx, (int)A.ny, (int)A.nz};
-                    bool hop = false;
-#pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        d[i] *= sg[i];
-                        float g = pf[i] + d[i];
-                        nf[i] = g;
-                        nv[i] = pv[i];
-                        if (g < 0.f || g >= 1.f) {
-                            float fl = floorf(g);
-                            int v = pv[i] + (int)fl;
-                            g -= fl;
-                            if (g >= 1.f) { g = 0.f; v += 1; }
-                            if (v < 0 || v >= n3[i]) { // FoV boundary (kernels.cu:133-136)
-                                if (A.cross_fov) {
-                                    v %= n3[i];
-                                    if (v < 0) v += n3[i];
-                                } else { // the step is reversed: new = old - rnd
-                                    g = pf[i] - d[i];
-                                    fl = floorf(g);
-                                    v = pv[i] + (int)fl;
-                                    g -= fl;
-                                    if (g >= 1.f) { g = 0.f; v += 1; }
-                                    if (v < 0 || v >= n3[i]) { g = pf[i]; v = pv[i]; } // |step| > distance to both walls: stay
-                                }
-                            }
-                            nf[i] = g;
-                            nv[i] = v;
-                            hop = true;
-                        }
-                    }
-                    ind_new = ind_cur;
-                    if (hop) ind_new = (int64_t)nv[0] * nyz + (int64_t)nv[1] * A.nz + nv[2];
-                    moved = fresh || ind_new != ind_cur;
                 }
-
-                if (moved) { // kernels.cu:150-170
+                const int64_t ix = (int64_t)__dmul_rn(nx_d[0], s2g[0]), iy = (int64_t)__dmul_rn(nx_d[1], s2g[1]),
+                              iz = (int64_t)__dmul_rn(nx_d[2], s2g[2]);
+                const int64_t ind_new = ix * nyz + iy * (int64_t)A.nz + iz; // kernels.cu:140
+                if (ind_new >= A.V || ind_new < 0) {                        // kernels.cu:141-147
+                    alive = false; lost = true;
+                    break;
+                }
+                if (fresh || ind_new != ind_cur) { // kernels.cu:150-170
                     if (STATS) st_mask++;
                     const uint32_t ts = __ldg(A.mask + ind_new);
                     float fv = has_field ? __ldg(A.fieldmap + ind_new) : 0.f; // issued together with the mask gather
                     if (ts != ts_old) {
-                        float u;
-                        if (MODE == SWK_MODE_COMPAT) u = minstd_uniform(rng_u);
-                        else u = u01_open1(philox4x32_10(ctr, 0u, spin_no, STREAM_PERMEABILITY, key0, key1).x);
-                        if (u >= tpXY[ts_old * L.n_sub + ts]) {
+                        if (minstd_uniform(rng_u) >= tpXY[ts_old * L.n_sub + ts]) {
                             if (STATS) st_rej++;
-                            if (MODE == SWK_MODE_FAST) ctr++;
                             if (itr++ > A.max_iter) { alive = false; lost = true; break; }
                             continue; // redo the step from the old position; time does not advance
                         }
                         ts_old = ts;
-                        if (MODE == SWK_MODE_COMPAT) sigma_d = tsigma[ts_old];
-                        else {
-#pragma unroll
-                            for (int i = 0; i < 3; i++) sg[i] = (float)(tsigma[ts_old] * (double)inv_h[i] / (double)fscale);
-                        }
                     }
                     if (STATS) st_field++;
                     ind_cur = ind_new;
@@ -502,26 +425,15 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
                     field = __fmul_rn(fv, field_k);       // monte_carlo.cu:244
                     T1 = tT1[ts_old];                     // kernels.cu:167-168 (ms -> s done on the host)
                     T2 = tT2[ts_old];
-                    if (MODE == SWK_MODE_COMPAT) sigma_d = tsigma[ts_old];
+                    sigma_d = tsigma[ts_old];
                 }
                 acc += field; // kernels.cu:171-172
                 itr = 0;
-                if (MODE == SWK_MODE_COMPAT) {
 #pragma unroll
-                    for (int i = 0; i < 3; i++) px[i] = nx_d[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) { pf[i] = nf[i]; pv[i] = nv[i]; }
-                    ctr++;
-                }
+                for (int i = 0; i < 3; i++) px[i] = nx_d[i];
                 if (A.record) { // kernels.cu:218-221
-                    if (MODE == SWK_MODE_COMPAT) {
 #pragma unroll
-                        for (int i = 0; i < 3; i++) xyz_f[i] = (float)px[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 3; i++) xyz_f[i] = (float)(((double)pv[i] + (double)pf[i]) / (double)inv_h[i] * (double)fscale);
-                    }
+                    for (int i = 0; i < 3; i++) xyz_f[i] = (float)px[i];
                     if (X1) {
                         float *slot = X1 + 3 * ((size_t)scan * n_tp + t);
                         slot[0] = xyz_f[0]; slot[1] = xyz_f[1]; slot[2] = xyz_f[2];
@@ -544,15 +456,8 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
                 if (alive) {
                     const float Gx = __fmul_rn(tgx[cnt_grad], gscale), Gy = __fmul_rn(tgy[cnt_grad], gscale),
                                 Gz = __fmul_rn(tgz[cnt_grad], gscale); // monte_carlo.cu:288-290
-                    double X, Y, Z;
-                    if (MODE == SWK_MODE_COMPAT) { X = px[0]; Y = px[1]; Z = px[2]; }
-                    else {
-                        X = ((double)pv[0] + (double)pf[0]) / (double)inv_h[0] * (double)fscale;
-                        Y = ((double)pv[1] + (double)pf[1]) / (double)inv_h[1] * (double)fscale;
-                        Z = ((double)pv[2] + (double)pf[2]) / (double)inv_h[2] * (double)fscale;
-                    }
                     // same association and contraction as the reference's SASS
-                    double g = __fma_rn((double)Gz, Z, __fma_rn((double)Gx, X, __dmul_rn((double)Gy, Y)));
+                    double g = __fma_rn((double)Gz, px[2], __fma_rn((double)Gx, px[0], __dmul_rn((double)Gy, px[1])));
                     g = __dmul_rn(g, 1e-3);
                     g = __dmul_rn(g, (double)A.timestep_us);
                     g = __dmul_rn(g, 1e-6);
@@ -577,25 +482,11 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
                 if (alive) {
                     const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
                     dephase_relax(m, acc, T1, T2, dt_s);
-                    if (M1) { M1[3 * cur_te + 0] = m[0]; M1[3 * cur_te + 1] = m[1]; M1[3 * cur_te + 2] = m[2]; }
-                    if (Tt) Tt[cur_te] = (uint8_t)ts_old;
+                    if (stage) stage[cur_te] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts_old);
                     acc = 0.f;
                     t_old = tp;
-                }
-                if (A.sums) { // ensemble sums per substrate: warp shuffle, then shared-memory accumulate
-                    const uint32_t lane = threadIdx.x & 31u;
-                    for (uint32_t sub = 0; sub < L.n_sub; sub++) {
-                        const bool mine = alive && ts_old == sub;
-                        const unsigned any = __ballot_sync(0xffffffffu, mine);
-                        if (!any) continue;
-                        float sx = warp_sum(mine ? m[0] : 0.f), sy = warp_sum(mine ? m[1] : 0.f), sz = warp_sum(mine ? m[2] : 0.f);
-                        if (lane == 0) {
-                            float *b = bsum + (cur_te * L.n_sub + sub) * 4u;
-                            atomicAdd(b + 0, sx); atomicAdd(b + 1, sy); atomicAdd(b + 2, sz);
-                            atomicAdd(b + 3, (float)__popc(any));
-                        }
-                    }
-                }
+                    if (A.sums_fx) echo_sums_add(bsum, cur_te * L.n_sub + ts_old, m);
+                } else if (stage) stage[cur_te] = make_uint4(0u, 0u, 0u, 0u); // abandoned spin: unwritten echoes read 0 (monte_carlo.cu:256,259-260)
                 cur_te++;
             }
         }
@@ -604,27 +495,22 @@ __global__ void __launch_bounds__(kBlock) walk_kernel(const WalkArgs A)
             const float dt_s = (float)((double)((n_tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
             dephase_relax(m, acc, T1, T2, dt_s);
         }
+        if (last_scan) echoes_done = cur_te;
     }
 
-    // ---- final position (kernels.cu:220-221 leaves the last committed position in xyz1) ----
-    if (!A.record && X1 && j < A.j_end) {
-        if (MODE == SWK_MODE_COMPAT) {
-#pragma unroll
-            for (int i = 0; i < 3; i++) xyz_f[i] = (float)px[i];
-        } else if (st_steps != 0 || !STATS) {
-#pragma unroll
-            for (int i = 0; i < 3; i++) xyz_f[i] = (float)(((double)pv[i] + (double)pf[i]) / (double)inv_h[i] * (double)fscale);
-        }
-        X1[0] = xyz_f[0]; X1[1] = xyz_f[1]; X1[2] = xyz_f[2];
+    // ---- final position (kernels.cu:220-221 leaves the last committed position in xyz1); echoes that never fired read 0 ----
+    if (stage) {
+        for (uint32_t e = echoes_done; e < A.n_te; e++) stage[e] = make_uint4(0u, 0u, 0u, 0u);
+        if (!A.record) stage[A.n_te] = make_uint4(__float_as_uint((float)px[0]), __float_as_uint((float)px[1]), __float_as_uint((float)px[2]), lost ? 1u : 0u);
     }
 
     // ---- flush block sums and counters ----
     __syncthreads();
-    if (A.sums) {
-        double *gs = A.sums + (size_t)k * n_bsum;
+    if (A.sums_fx) {
+        unsigned long long *gs = A.sums_fx + (size_t)k * n_bsum;
         for (uint32_t i = threadIdx.x; i < n_bsum; i += kBlock) {
-            float v = bsum[i];
-            if (v != 0.f) atomicAdd(gs + i, (double)v);
+            const long long v = bsum[i];
+            if (v != 0) atomicAdd(gs + i, (unsigned long long)v);
         }
     }
     if (A.counters) {

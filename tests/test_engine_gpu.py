@@ -151,7 +151,7 @@ def test_shards_are_invariant(sw, mode_name):
     for key in ("M1", "XYZ1", "T"):
         cat = np.concatenate([p[key] for p in parts], axis=1)
         assert np.array_equal(cat, full[key]), key
-    assert np.allclose(parts[0]["sums"] + parts[1]["sums"], full["sums"], rtol=1e-6, atol=1e-4)
+    assert np.array_equal(parts[0]["sums"] + parts[1]["sums"], full["sums"])  # fixed-point sums: exact, whatever the split
 
 
 def test_device_resident_run_and_device_positions(sw):
@@ -286,7 +286,7 @@ def test_rebinned_long_run_equals_uninterrupted_run(sw, oracle, monkeypatch, sca
     assert np.allclose(ref[3], got[3], rtol=1e-6, atol=1e-3)
     for key in ("steps", "mask_gathers", "field_gathers", "rejects", "lost"):
         assert st0[key] == st1[key], key
-    assert st2["n_launches"] == 1
+    assert st2["n_launches"] <= 3  # one walk launch (+ the unpack pass and the conversion of the sums)
 
 
 @pytest.mark.parametrize("name", ["se", "multi_echo", "events_edge"])
@@ -334,9 +334,9 @@ def test_single_spin_and_ragged_sizes(sw, oracle):
 
 
 def test_zslab_walks_the_same_path(sw):
-    """SWK_RUN_ZSLAB (opt-in): a phantom whose mask and field map do not depend on z — every cylinder phantom — is walked on the packed
-    words of one z plane.  They are the words of the full table, so the results are the default FAST results bit for bit; a phantom
-    that does depend on z ignores the flag."""
+    """A phantom whose mask and field map do not depend on z — every cylinder phantom — is walked on the packed words of ONE z plane (the
+    default; SWK_RUN_NO_ZSLAB keeps the full [nx][ny][nz] table).  They are the words of the full table, so the results are the full-table
+    results bit for bit; a phantom that does depend on z takes the full table either way."""
     case, mask, fm, fov, xyz0 = cases.se(n_spins=900)
     assert (mask == mask[:, :, :1]).all() and (fm.view(np.uint32) == fm[:, :, :1].view(np.uint32)).all(), "the test phantom must be z-invariant"
     cfg = cases.to_simconfig(case)
@@ -344,28 +344,89 @@ def test_zslab_walks_the_same_path(sw):
         e.set_phantom(mask, fm, fov)
         e.set_sequence(cfg)
         e.set_spins(xyz0)
-        st0 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS)
+        st0 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_NO_ZSLAB)
         base = e.download() + (e.sums(),)
-        st1 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_ZSLAB)
+        st1 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS)
         slab = e.download() + (e.sums(),)
-        st2 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_ZSLAB)
-    assert st1["n_launches"] == 3 and st2["n_launches"] == 1  # z-invariance check + slab packing happen once per phantom
-    for a, b in zip(base[:3], slab[:3]):
-        assert np.array_equal(a, b)
-    assert np.allclose(base[3], slab[3], rtol=1e-9, atol=1e-3)
+        st2 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL)
+    assert st1["n_launches"] == st2["n_launches"] + 2  # z-invariance check + slab packing happen once per phantom
+    for a, b in zip(base, slab):
+        assert np.array_equal(a, b)  # (the sums too: they are accumulated in integer fixed point)
     for key in ("steps", "mask_gathers", "field_gathers", "rejects", "lost"):
         assert st0[key] == st1[key], key
-    # not invariant along z: the flag changes nothing
+    # not invariant along z: the full table, whatever the flag
     case, mask, fm, fov, xyz0 = cases.multi_echo(n_spins=400)
     cfg = cases.to_simconfig(case)
     with sw.Engine(0) as e:
         e.set_phantom(mask, fm, fov)
         e.set_sequence(cfg)
         e.set_spins(xyz0)
-        e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL)
+        st_a = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL)
         base = e.download()
-        st = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_ZSLAB)
+        st_b = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_NO_ZSLAB)
         again = e.download()
-    assert st["n_launches"] == 2  # the check itself, then the normal table
+    assert st_a["n_launches"] >= st_b["n_launches"]  # the check itself ran in the first run only
     for a, b in zip(base, again):
         assert np.array_equal(a, b)
+
+
+def test_shared_and_private_streams_agree(sw):
+    """The SHARED kernel variant (a block walks 32 spins x G scales and generates each spin's normals once) and the PRIVATE one (every thread
+    generates its own) draw the same numbers for the same (spin, round): identical outputs, sums and counters — FoV, gradient and phase scaling."""
+    for name in ("gre", "pgse", "ssfp", "multi_echo", "ragged"):
+        case, mask, fm, fov, xyz0 = cases.ALL[name]()
+        cfg = cases.to_simconfig(case)
+        with sw.Engine(0) as e:
+            e.set_phantom(mask, fm, fov)
+            e.set_sequence(cfg)
+            e.set_spins(xyz0)
+            st0 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS)
+            shared = e.download() + (e.sums(),)
+            st1 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_NO_SHARE)
+            private = e.download() + (e.sums(),)
+        for a, b in zip(shared, private):
+            assert np.array_equal(a, b), name
+        for key in ("steps", "mask_gathers", "field_gathers", "rejects", "lost"):
+            assert st0[key] == st1[key], (name, key)
+
+
+def test_scales_do_not_depend_on_their_neighbours(sw):
+    """Like the reference, which launches every scale on its own (monte_carlo.cu:273-337), the result of a scale does not depend on which
+    other scales are simulated with it (block composition, group size of the SHARED variant): 13 scales at once == each scale alone."""
+    case, mask, fm, fov, xyz0 = cases.gre(n_spins=300, scales=tuple(0.05 * 1.5 ** i for i in range(13)))
+    cfg = cases.to_simconfig(case)
+    with sw.Engine(0) as e:
+        e.set_phantom(mask, fm, fov)
+        e.set_sequence(cfg)
+        e.set_spins(xyz0)
+        e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL)
+        m1, x1, t = e.download()
+        sums = e.sums()
+        for k in (0, 5, 12):
+            e.run_device(scales=[case.scales[k]], mode=sw.MODE_FAST, flags=sw.OUT_ALL)
+            a, b, c = e.download()
+            assert np.array_equal(a[0], m1[k]) and np.array_equal(b[0], x1[k]) and np.array_equal(c[0], t[k])
+            assert np.array_equal(e.sums()[0], sums[k])
+
+
+def test_row_copies_beyond_the_pitch_limit(sw, monkeypatch):
+    """cudaMemcpy2D rejects pitches above cudaDeviceProp::memPitch (2^31 - 1): per-scale blocks of 2 GiB or more (1e8 spins x 2 echoes,
+    trajectories) are copied scale by scale instead.  SWK_MEMPITCH fakes a tiny limit so that a test-sized run takes that path: several engines
+    filling one set of host arrays (swk_set_host_rows), plain and sliced."""
+    monkeypatch.setenv("SWK_MEMPITCH", "64")
+    case, mask, fm, fov, xyz0 = cases.multi_echo(n_spins=1100)
+    cfg = cases.to_simconfig(case)
+    full = _run_engine(sw, case, mask, fm, fov, xyz0, sw.MODE_FAST)
+    K, S, E = case.n_scales, case.n_spins, case.n_TE
+    for slices in (None, "3"):
+        if slices:
+            monkeypatch.setenv("SWK_SLICES", slices)
+        out = (np.zeros((K, S, E, 3), np.float32), np.zeros((K, S, 1, 3), np.float32), np.zeros((K, S, E), np.uint8))
+        for first, n in ((0, 300), (300, 800)):
+            with sw.Engine(0) as e:
+                e.set_phantom(mask, fm, fov)
+                e.set_sequence(cfg)
+                e._ck(e._lib.swk_set_host_rows(e._h, S, first))
+                e.run(xyz0[first:first + n], spin_first=first, mode=sw.MODE_FAST, out=out)
+        for a, key in zip(out, ("M1", "XYZ1", "T")):
+            assert np.array_equal(a, full[key]), (slices, key)

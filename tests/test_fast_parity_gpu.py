@@ -1,0 +1,273 @@
+"""SWK_MODE_FAST (the benchmarked path) against the reference's OWN cu_sim kernel (unmodified src/sim/kernels.cu compiled for sm_100a,
+oracle/_ref/libswref_cuda.so) on BASELINE.json's configs, same GPU, same phantom (the product generator's, bit-identical to
+`spinwalk phantom`), same start positions.  FAST is another random stream, so parity is the ensemble tier of SURVEY §8c (T2), as tight as the
+Monte-Carlo error allows and WITHOUT the 2e-3 slack of the small-sample test in test_engine_gpu.py:
+
+    per (scale, echo, substrate) and component:  |mean_fast - mean_ref| <= 4 sqrt(SE_fast^2 + SE_ref^2) + 2e-4
+    SE^2 = Var(component) / N over the spins found in that substrate at the echo;
+    tissue occupancy at the echo within 4 binomial standard errors; lost-spin counts equal.
+
+The 2e-4 floor covers what is NOT sampling noise: FP32 event arithmetic and the 20-bit field of the packed voxel word (relative 2^-21 of the
+accrued phase); at large FoV scales every spin carries nearly the same magnetisation and SE itself drops below 1e-5.
+Each test prints the largest |delta| / SE it saw (pytest -s, or the assertion message on failure).
+
+C1 runs at FULL size (1e5 spins x 50 scales); C2, C3, C3r and a shortened C4 on 1e6-spin samples (reference cu_sim: ~2.8e10 spin-steps/s).
+FAST never abandons a spin whose step exceeds BOTH FoV walls (it keeps the axis); the reference computes an out-of-range index and
+drops the spin (kernels.cu:141-147).  That only happens where the scaled FoV is a few step lengths wide (C1: FoV scales < 0.04, i.e. FoV < 4 um);
+those scales are compared on the spins the reference kept, and the reference's loss count is printed.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FLOOR = 2e-4
+NSIG = 4.0
+
+
+def _stats(M1, T, n_sub):
+    """per (scale, echo, substrate): mean [K,E,ns,3], SE [K,E,ns,3], count [K,E,ns]; spins whose echo was never written (lost: all three
+    components exactly 0, monte_carlo.cu:256) are left out."""
+    K, S, E, _ = M1.shape
+    mean = np.zeros((K, E, n_sub, 3))
+    se = np.zeros((K, E, n_sub, 3))
+    cnt = np.zeros((K, E, n_sub))
+    written = (M1 != 0).any(axis=3)
+    for k in range(K):
+        for e in range(E):
+            for s in range(n_sub):
+                w = written[k, :, e] & (T[k, :, e] == s)
+                n = int(w.sum())
+                cnt[k, e, s] = n
+                if n < 2:
+                    continue
+                m = M1[k, w, e, :].astype(np.float64)
+                mean[k, e, s] = m.mean(axis=0)
+                se[k, e, s] = np.sqrt(m.var(axis=0) / n)
+    return mean, se, cnt
+
+
+def _compare(name, fast, ref, n_sub, scales, min_count=200):
+    mf, sf, cf = _stats(fast["M1"], fast["T"], n_sub)
+    mr, sr, cr = _stats(ref["M1"], ref["T"], n_sub)
+    S = fast["M1"].shape[1]
+    ok = (cf >= min_count) & (cr >= min_count)
+    comb = np.sqrt(sf**2 + sr**2)
+    d = np.abs(mf - mr)
+    excess = np.where(ok[..., None], d - (NSIG * comb + FLOOR), -1.0)
+    z = np.where(ok[..., None], (d - FLOOR).clip(min=0) / np.maximum(comb, 1e-12), 0.0)
+    k, e, s, c = np.unravel_index(np.argmax(z), z.shape)
+    # transverse signal magnitude of the whole population per (scale, echo): what a vessel-size / b-value curve plots
+    tot_f = (mf * cf[..., None]).sum(axis=2) / np.maximum(cf.sum(axis=2), 1)[..., None]
+    tot_r = (mr * cr[..., None]).sum(axis=2) / np.maximum(cr.sum(axis=2), 1)[..., None]
+    sig_f, sig_r = np.hypot(tot_f[..., 0], tot_f[..., 1]), np.hypot(tot_r[..., 0], tot_r[..., 1])
+    print(f"\n[{name}] {S} spins x {len(scales)} scales: max (|delta| - floor) / SE = {z.max():.2f} at scale {scales[k]:g} echo {e} substrate {s} "
+          f"component {'xyz'[c]} (delta {d[k, e, s, c]:.3g}, SE {comb[k, e, s, c]:.3g}); max |d|S|| = {np.abs(sig_f - sig_r).max():.3g}; "
+          f"|S| fast {np.array2string(sig_f[:, -1], precision=4, max_line_width=400)} ref {np.array2string(sig_r[:, -1], precision=4, max_line_width=400)}")
+    assert (excess <= 0).all(), (f"{name}: ensemble mismatch, worst {z.max():.2f} SE at scale {scales[k]:g} echo {e} substrate {s} component {'xyz'[c]}: "
+                                 f"fast {mf[k, e, s, c]:.6f} ref {mr[k, e, s, c]:.6f} SE {comb[k, e, s, c]:.2e}")
+    # tissue occupancy at the echo (fraction of the written spins found in each substrate)
+    pf, pr = cf / np.maximum(cf.sum(axis=2, keepdims=True), 1), cr / np.maximum(cr.sum(axis=2, keepdims=True), 1)
+    tol = NSIG * np.sqrt((pr * (1 - pr) + pf * (1 - pf)) / S) + 1e-6
+    assert (np.abs(pf - pr) <= tol).all(), f"{name}: tissue occupancy differs by {np.abs(pf - pr).max():.3g} (tolerance {tol.max():.3g})"
+    return z.max()
+
+
+def _setup(workload, n_spins, scales_pick=None, **override):
+    import bench
+    import spinwalk_b200 as sw
+    from oracle import pyoracle as po
+
+    if not po.have_ref_cuda():
+        pytest.skip("oracle/_ref/libswref_cuda.so not present")
+    cfg_kw, ph, _ = bench.workload(workload, n_spins, None)
+    cfg_kw.update(override)
+    if scales_pick is not None:
+        cfg_kw["scales"] = [cfg_kw["scales"][i] for i in scales_pick]
+    eng = sw.Engine(0)
+    eng.generate_phantom(bench.phantom_spec(ph))
+    mask, fm = eng.get_phantom()
+    fov = eng.fov
+    xyz0 = bench.make_positions(n_spins, fov, cfg_kw["seed"])
+    cfg = sw.SimConfig(**cfg_kw)
+    eng.set_sequence(cfg)
+    case = bench.oracle_case(cfg_kw, ph["n"], fov, n_spins)
+    case.n_dummy_scan = eng.n_dummy_scan
+    return sw, po, eng, cfg, case, mask, fm, fov, xyz0
+
+
+def test_c1_full_size_vs_reference_cu_sim(engine_lib):
+    """BASELINE configs[0] at full size: GRE, 100^3 cylinder phantom, 1e5 spins x the 50 FoV scales of config_default.ini."""
+    sw, po, eng, cfg, case, mask, fm, fov, xyz0 = _setup("c1", 100_000)
+    with eng:
+        fast = eng.run(xyz0, mode=sw.MODE_FAST)
+    ref = po.run_ref_cuda(case, fm, mask, xyz0)
+    scales = np.asarray(cfg.scales)
+    lost_ref = (~(ref["M1"] != 0).any(axis=3)).sum(axis=(1, 2))
+    print(f"\n[c1] reference lost spins per scale (double wrap, FoV < 4 um): {dict((float(s), int(n)) for s, n in zip(scales, lost_ref) if n)}")
+    assert fast["stats"]["lost"] == 0
+    assert (lost_ref[scales >= 0.046] == 0).all(), "the reference loses spins only where the FoV is a few step lengths wide"
+    _compare("c1", fast, ref, 2, scales)
+
+
+def test_c2_sample_vs_reference_cu_sim(engine_lib):
+    """BASELINE configs[1] (the bench headline): SE BOLD, 600^3 phantom + field map; 1e6 of the 1e7 spins x every 5th FoV scale."""
+    pick = list(range(0, 50, 5))
+    sw, po, eng, cfg, case, mask, fm, fov, xyz0 = _setup("c2", 1_000_000, scales_pick=pick)
+    with eng:
+        fast = eng.run(xyz0, mode=sw.MODE_FAST)
+        full = None
+        eng.set_spins(xyz0)
+        eng.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_NO_ZSLAB)  # the full [nx][ny][nz] table walks the same path as the z slab
+        full = eng.download()
+    ref = po.run_ref_cuda(case, fm, mask, xyz0)
+    assert fast["stats"]["lost"] == 0 and (ref["M1"] != 0).any(axis=3).all()
+    for a, b in zip((fast["M1"], fast["XYZ1"], fast["T"]), full):
+        assert np.array_equal(a, b), "z-slab and full-table walks differ"
+    _compare("c2", fast, ref, 2, np.asarray(cfg.scales))
+    # impermeable walls: nobody changes substrate, in either implementation
+    assert np.array_equal(fast["T"][0], fast["T"][-1]) and np.array_equal(ref["T"][0], fast["T"][0])
+
+
+@pytest.mark.parametrize("workload", ["c3", "c3r"])
+def test_c3_pgse_sample_vs_reference_cu_sim(engine_lib, workload):
+    """BASELINE configs[2]: PGSE on the 400^3 permeable-sphere phantom (free: P_XY = 1; restricted: P_XY = 0.05), CROSS_FOV = 1;
+    1e6 of the 1e7 spins x 6 of the 51 gradient scales (b = 100, 1000, 2500, 4000, 5000, 0)."""
+    pick = [0, 9, 24, 39, 49, 50]
+    sw, po, eng, cfg, case, mask, fm, fov, xyz0 = _setup(workload, 1_000_000, scales_pick=pick)
+    with eng:
+        fast = eng.run(xyz0, mode=sw.MODE_FAST)
+    ref = po.run_ref_cuda(case, fm, mask, xyz0)
+    assert fast["stats"]["lost"] == 0 and (ref["M1"] != 0).any(axis=3).all()
+    _compare(workload, fast, ref, 2, np.asarray(cfg.scales))
+
+
+def test_c4_shortened_vs_reference_cu_sim(engine_lib):
+    """BASELINE configs[3] shortened: bSSFP (config/ssfp.ini: TR 10 ms, FA 16, linear phase cycling 180) with 100 dummy scans instead of
+    5 T1 / TR = 1101 (20 200 steps per spin instead of 220 200), 1e6 spins, FoV scale 1 and phase cycling as generate_bssfp writes it."""
+    sw, po, eng, cfg, case, mask, fm, fov, xyz0 = _setup("c4", 1_000_000, n_dummy_scan=100)
+    assert eng.n_dummy_scan == 100
+    with eng:
+        fast = eng.run(xyz0, mode=sw.MODE_FAST)
+    ref = po.run_ref_cuda(case, fm, mask, xyz0)
+    assert fast["stats"]["lost"] == 0 and (ref["M1"] != 0).any(axis=3).all()
+    _compare("c4", fast, ref, 2, np.asarray(cfg.scales))
+
+
+def test_fast_trajectory_recording(sw_mod, oracle):
+    """RECORD_TRAJECTORY in FAST mode (kernels.cu:218-221; the RECORD = true kernel variants): the recorded walk IS the walk — its last
+    sample equals the final position of the same run without recording (same random stream), M1 / T are unchanged, slot (scan, t) holds the
+    position after step t, consecutive samples are one Gaussian step apart — and its mean squared displacement follows the oracle's."""
+    import cases
+
+    sw = sw_mod
+    case, mask, fm, fov, xyz0 = cases.trajectory(n_spins=4000)
+    cfg = cases.to_simconfig(case)
+    with sw.Engine(0) as e:
+        e.set_phantom(mask, fm, fov)
+        e.set_sequence(cfg)
+        rec = e.run(xyz0, mode=sw.MODE_FAST)
+        cfg.record_trajectory = 0
+        e.set_sequence(cfg)
+        plain = e.run(xyz0, mode=sw.MODE_FAST)
+    K, S = case.n_scales, case.n_spins
+    n_tp, R = case.n_timepoints, case.n_dummy + 1
+    assert rec["XYZ1"].shape == (K, S, n_tp * R, 3) and plain["XYZ1"].shape == (K, S, 1, 3)
+    assert np.array_equal(rec["M1"], plain["M1"]) and np.array_equal(rec["T"], plain["T"])
+    assert np.array_equal(rec["XYZ1"][:, :, -1, :], plain["XYZ1"][:, :, 0, :]), "the last recorded sample is the final position"
+    assert rec["stats"]["lost"] == 0 and np.isfinite(rec["XYZ1"]).all()
+    ora = oracle.run_oracle(case, fm, mask, xyz0, flavour=oracle.RNG_MINSTD)
+    sigma = 1e-3 * np.sqrt(2 * 1e-9 * case.timestep_us)
+    for k, s in enumerate(case.scales):
+        x = rec["XYZ1"][k].astype(np.float64)
+        f = np.asarray(fov, np.float64) * s
+        assert (x >= 0).all() and (x < f * (1 + 1e-6)).all()
+        step = np.diff(x, axis=1)
+        assert np.abs(step).max() <= 5.7 * sigma * 2 + 1e-9  # a reversed step at a FoV wall (kernels.cu:133-136) is still one draw long
+        # most steps are free: per-axis rms of one step == sigma (impermeable walls only reject, they never shorten a step)
+        assert abs(step.std() / sigma - 1.0) < 0.03
+        # mean squared displacement from the start, FAST vs oracle, at a few timepoints
+        x0 = xyz0.astype(np.float64) * np.float32(s)
+        xo = ora["XYZ1"][k].astype(np.float64)
+        for t in (0, 9, 49, n_tp * R - 1):
+            a, b = ((x[:, t] - x0) ** 2).sum(axis=1), ((xo[:, t] - x0) ** 2).sum(axis=1)
+            se = np.sqrt(a.var() / S + b.var() / S)
+            assert abs(a.mean() - b.mean()) <= NSIG * se, (s, t, a.mean(), b.mean(), se)
+
+
+def test_fast_stuck_spins(sw_mod, oracle):
+    """The FAST lost-spin exit (kernels.cu:155-159: more than MAX_ITERATIONS consecutive permeability rejections): with MAX_ITERATIONS = 3 on a
+    fine impermeable checkerboard a large share of the spins is abandoned.  The share must match the oracle's within binomial error, an abandoned
+    spin keeps the echoes it had written and reads 0 for the later ones, and its XYZ1 is its last committed position."""
+    import cases
+
+    sw = sw_mod
+    S = 20000
+    case, mask, fm, fov, xyz0 = cases.stuck(n_spins=S)
+    case.scales = [1.0, 1.7]  # (the case's 0.02 scale loses spins to double wraps in the reference, which FAST does not do)
+    cfg = cases.to_simconfig(case)
+    with sw.Engine(0) as e:
+        e.set_phantom(mask, fm, fov)
+        e.set_sequence(cfg)
+        got = e.run(xyz0, mode=sw.MODE_FAST)
+    ora = oracle.run_oracle(case, fm, mask, xyz0, flavour=oracle.RNG_MINSTD)
+    wg, wo = (got["M1"] != 0).any(axis=3), (ora["M1"] != 0).any(axis=3)  # [K,S,E] echo written
+    assert (wg[:, :, 0] | ~wg[:, :, 1]).all(), "a later echo is written only if the earlier one was"
+    lost_g, lost_o = (~wg[:, :, -1]).sum(), (~wo[:, :, -1]).sum()
+    assert got["stats"]["lost"] >= lost_g  # (a spin abandoned after the last echo has written every echo)
+    n_pairs = wg[:, :, -1].size
+    pl_g, pl_o = got["stats"]["lost"] / n_pairs, ora["stats"]["lost"] / n_pairs
+    assert abs(pl_g - pl_o) <= NSIG * np.sqrt((pl_g * (1 - pl_g) + pl_o * (1 - pl_o)) / n_pairs) + 1e-4, (pl_g, pl_o)
+    assert lost_o > 0.05 * wo[:, :, -1].size, "the case must exercise the exit"
+    for k in range(case.n_scales):
+        for e_ in range(case.n_TE):
+            pg, po_ = 1 - wg[k, :, e_].mean(), 1 - wo[k, :, e_].mean()
+            tol = NSIG * np.sqrt((pg * (1 - pg) + po_ * (1 - po_)) / S) + 1e-4
+            assert abs(pg - po_) <= tol, f"lost share at scale {case.scales[k]} echo {e_}: fast {pg:.4f} oracle {po_:.4f} (tolerance {tol:.4f})"
+    assert (got["T"][~wg] == 0).all()
+    f = np.asarray(fov, np.float64)
+    for k, s in enumerate(case.scales):
+        x = got["XYZ1"][k, :, 0, :]
+        assert (x >= 0).all() and (x < f * s * (1 + 1e-6)).all()
+    # the survivors' ensemble still matches
+    _compare("stuck", got, ora, 2, np.asarray(case.scales), min_count=500)
+
+
+@pytest.fixture(scope="module")
+def sw_mod(engine_lib):
+    import spinwalk_b200 as sw
+
+    assert engine_lib.swk_device_count() > 0
+    return sw
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_random_cases_vs_reference_cu_sim(sw_mod, oracle, chunk):
+    """The seeded random cases of tests/random_cases.py (the CPU oracle is pinned on them, test_oracle_random.py) through the engine:
+    COMPAT must equal the reference's cu_sim — T and XYZ1 bitwise, M1 <= 2e-6 — over the whole parameter space (1-4 substrates, every scale
+    type and boundary rule, coinciding / out-of-TR events, zero diffusivity, tiny MAX_ITERATIONS, trajectories); FAST must run every case
+    to finite outputs of the right shape, RECORD variants included."""
+    import cases
+    import random_cases
+
+    sw = sw_mod
+    if not oracle.have_ref_cuda():
+        pytest.skip("oracle/_ref/libswref_cuda.so not present")
+    bad = []
+    for seed in range(chunk * 25, chunk * 25 + 25):
+        case, mask, fm, fov, xyz0 = random_cases.make(seed)
+        ref = oracle.run_ref_cuda(case, fm, mask, xyz0)
+        cfg = cases.to_simconfig(case)
+        with sw.Engine(0) as e:
+            e.set_phantom(mask, fm, fov)
+            e.set_sequence(cfg)
+            got = e.run(xyz0, mode=sw.MODE_COMPAT)
+            fast = e.run(xyz0, mode=sw.MODE_FAST)
+        okT = np.array_equal(got["T"], ref["T"])
+        okX = np.array_equal(got["XYZ1"].view(np.uint32), ref["XYZ1"].view(np.uint32))
+        dM = float(np.abs(got["M1"] - ref["M1"]).max()) if got["M1"].size else 0.0
+        okF = bool(np.isfinite(fast["M1"]).all() and np.isfinite(fast["XYZ1"]).all() and fast["M1"].shape == ref["M1"].shape
+                   and fast["XYZ1"].shape == ref["XYZ1"].shape and (np.abs(fast["M1"]) <= 1.0 + 1e-5).all())
+        if not (okT and okX and dM <= 2e-6 and okF):
+            bad.append((seed, okT, okX, dM, okF))
+    assert not bad, f"random cases differing from the reference cu_sim (seed, T, XYZ1, max|dM1|, fast finite): {bad}"
