@@ -467,6 +467,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "compat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (full_table, compat, scale_groups, non_invariant, north_star)")
     args = ap.parse_args()
     protect_stdout()
     if args.workload == "ph-mesh":
@@ -478,14 +479,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     cfg_kw, ph, desc = workload(args.workload, args.spins or None, args.scales or None)
-    S_per_gpu = cfg_kw["n_spins"]
-    K = len(cfg_kw["scales"])
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        mask2, fm2, fov = make_phantom_2d(ph)
+        mask2, fm2, fov = reference_phantom(ph)
         vals, samples = [], None
         tgt = 12.0
         for i in range(args.warmup + args.steps):
@@ -500,7 +499,8 @@ def main():
         emit({"impl": "reference", "metric": "spin-steps/s", "value": v, "unit": "spin-steps/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / max(1, args.steps),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
-                          "data": "synthetic", "config": {"workload": desc, "note": "each step = bounded sample of the workload on host cores"},
+                          "data": "synthetic", "config": {"workload": desc, "note": "each step = bounded sample of the workload on host cores; the phantom is "
+                                                          "the recipe's own (oracle restatement of `spinwalk phantom`, bit-identical to what the GPU arm generates)"},
                           "cpu_baseline": samples, "gpu_launches": 0,
                           "e2e": {"value": v, "unit": "spin-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
@@ -510,7 +510,6 @@ def main():
     import torch.distributed as dist
 
     import spinwalk_b200 as sw
-    from spinwalk_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
@@ -518,167 +517,380 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
+    W = Walk(sw, torch, dist, dev, rank, world, local_rank)
     mode = sw.MODE_FAST if args.mode == "fast" else sw.MODE_COMPAT
-    cfg_kw_global = dict(cfg_kw, n_spins=S_per_gpu * world)  # weak scaling: global population grows with N
-    cfg = sw.SimConfig(**cfg_kw_global)
-    # the phantom: the reference's own recipe (`spinwalk phantom ...`), generated on every rank's device by the product generator
-    # (include/spinwalk_phantom.h: bit-identical to the reference's generator, tests/test_phantom_gpu.py) — it never visits the host
-    eng = sw.Engine(local_rank)
-    gen = eng.generate_phantom(phantom_spec(ph))
-    fov = eng.fov
+    peak, peak_src = measured_peaks()
 
-    spin_first, n_local = sharding.shard_range(S_per_gpu * world, rank, world)  # weak scaling: S_per_gpu spins on every rank
-    assert n_local == S_per_gpu
-    xyz0_pin = torch.empty((S_per_gpu, 3), dtype=torch.float32, pin_memory=True)
-    xyz0_pin.numpy()[:] = make_positions(S_per_gpu, fov, cfg.seed, spin_first)
+    # ---- the headline workload
+    H = W.setup(args.workload, cfg_kw, ph)
     per_spin_out = args.workload != "c5"  # C5: 1e9 spins x 50 scales of per-spin output would be 650 GB: the reduce is the product
     out_flags = sw.OUT_ALL if per_spin_out else 0
-    eng.set_sequence(cfg)
-    eng.set_spins(xyz0_pin.numpy(), None, spin_first)
-    E, ns = cfg.n_TE, cfg.n_substrate
-    sums_d = torch.zeros((K, E, ns, 4), dtype=torch.float64, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def one_pass():
-        st = eng.run_device(mode=mode, flags=out_flags, d_sums_ptr=sums_d.data_ptr())
-        sharding.allreduce_sums(sums_d)  # the one collective of the path: a few KB of per-echo ensemble sums (NCCL)
-        return st
-
-    # counters (voxel changes etc.) for the roofline's algorithmic bytes: same inputs, STATS kernel variant, untimed
-    st_counts = eng.run_device(mode=mode, flags=out_flags | sw.RUN_STATS, d_sums_ptr=sums_d.data_ptr())
-
-    for _ in range(args.warmup):
-        one_pass()
-    barrier()
-    dev_ms, ker_ms = 0.0, 0.0
+    counts = W.counts(H, mode, out_flags)
     with ClockSampler(local_rank) as clk:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            st = one_pass()
-            dev_ms += st["device_ms"]
-            ker_ms += st["kernel_ms"]
-        barrier()
-        wall_s = time.perf_counter() - t0
+        T = W.timed(H, mode, out_flags, args.steps, args.warmup)
     clocks = clk.summary()
-    t = torch.tensor([dev_ms, ker_ms, wall_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, ker_ms, wall_ms = (float(v) for v in t.tolist())
-    steps_per_pass_rank = S_per_gpu * K * (eng.n_dummy_scan + 1) * cfg.n_timepoints
-    total_steps = steps_per_pass_rank * world * args.steps
-    value = total_steps / (dev_ms * 1e-3)
+    K, E, ns, S_per_gpu = H["K"], H["E"], H["ns"], H["S"]
+    value = H["steps_per_pass"] * world * args.steps / (T["dev_ms"] * 1e-3)
 
-    # ---- end-to-end through swk_run with host buffers
     e2e = None
     if not args.no_e2e:
-        if per_spin_out:
-            out = (torch.empty((K, S_per_gpu, E, 3), dtype=torch.float32, pin_memory=True),
-                   torch.empty((K, S_per_gpu, eng.trj, 3), dtype=torch.float32, pin_memory=True),
-                   torch.empty((K, S_per_gpu, E), dtype=torch.uint8, pin_memory=True))
-            out_np = tuple(o.numpy() for o in out)
-        else:
-            out, out_np = (), None
-        h2d = xyz0_pin.numel() * 4 + K * 4
-        d2h = sum(o.numel() * o.element_size() for o in out) + K * E * ns * 4 * 8
-        eng.run(xyz0_pin.numpy(), None, spin_first, mode=mode, out=out_np, outputs=per_spin_out, stats=False)  # warm
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r = eng.run(xyz0_pin.numpy(), None, spin_first, mode=mode, out=out_np, outputs=per_spin_out, stats=False)
-            if world > 1:
-                sums_d.copy_(torch.from_numpy(r["sums"]))
-                sharding.allreduce_sums(sums_d)
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_steps / float(te.item()), "unit": "spin-steps/s", "h2d_bytes_per_step": h2d * world,
-               "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * float(te.item()) / args.steps,
-               "api": "swk_run (C-ABI) with pinned host buffers: XYZ0 in; " + ("M1, XYZ1, T, sums out" if per_spin_out else "sums out")}
-        del out, out_np
-
-    # ---- the voxel fetch's own roofline, measured live on this device and this phantom (untimed diagnostic launch)
-    try:
-        probe = eng.probe_gather(threads_per_sm=2048, iters=2048)
-    except Exception as ex:  # a diagnostic must never cost the bench line
-        probe = {"gathers_per_s": None, "table_bytes": None, "error": str(ex)}
+        e2e = W.e2e(H, mode, per_spin_out, args.steps)
 
     # ---- roofline of the walk kernel: algorithmic bytes / mean launch duration
-    peak, peak_src = measured_peaks()
-    traffic, traffic_src = None, None
-    try:  # DRAM bytes per launch of this very workload from the committed ncu capture (profiles/traffic.json)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tj.get(f"{args.workload}:{args.mode}")
-        if ent and not args.scales and (not args.spins or ent.get("spins_per_gpu")):
-            # a capture taken with fewer spins scales linearly (every spin does the same work on average)
-            traffic = ent["dram_bytes_per_launch"] * (S_per_gpu / ent["spins_per_gpu"] if ent.get("spins_per_gpu") else 1.0)
-            traffic_src = ent["source"]
-    except Exception:
-        pass
-    per_pass_bytes = (st_counts["mask_gathers"] * 1 + st_counts["field_gathers"] * 4
-                      + S_per_gpu * K * (24 + ((13 * E + 12) if per_spin_out else 0)))
-    ker_ms_per_launch = ker_ms / args.steps
-    achieved = per_pass_bytes / (ker_ms_per_launch * 1e-3) / 1e9
-    fetches_per_s = st_counts["mask_gathers"] / (ker_ms_per_launch * 1e-3)
-    gather = {"voxel_fetches_per_s": fetches_per_s, "random_gather_peak_per_s": probe.get("gathers_per_s"),
-              "frac_of_random_gather_peak": (fetches_per_s / probe["gathers_per_s"]) if probe.get("gathers_per_s") else None,
-              "table_bytes": probe.get("table_bytes"),
-              "hbm_64B_fetches_per_s": (traffic / 64 / (ker_ms_per_launch * 1e-3)) if traffic else None,
-              # the probe's own HBM rate: its gathers minus the share a uniformly random access finds in L2 (L2 bytes / table bytes)
-              "hbm_fetch_frac_of_probe": (traffic / 64 / (ker_ms_per_launch * 1e-3) / (probe["gathers_per_s"] * max(0.05, 1.0 - 126e6 / probe["table_bytes"])))
-              if (traffic and probe.get("gathers_per_s") and probe.get("table_bytes")) else None,
-              "note": "random_gather_peak = swk_probe_gather: dependent random 4-byte gathers over the same voxel table, nothing else "
-                      "(HBM row-activation bound, DESIGN.md §5); voxel_fetches include L1/L2 hits of the larger FoV scales"}
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src, "gather": gather,
-                "peak_source": peak_src, "kernel": "swk::walk_fast_kernel" if mode == sw.MODE_FAST else "swk::walk_kernel<COMPAT>",
-                "algorithmic_bytes_per_launch": per_pass_bytes, "kernel_ms_per_launch": ker_ms_per_launch,
-                "bytes_per_spin_step": per_pass_bytes / steps_per_pass_rank,
-                "p_voxel_change": st_counts["mask_gathers"] / max(1, st_counts["steps"]),
-                "rejects_per_step": st_counts["rejects"] / max(1, st_counts["steps"]),
-                "note": "gather-latency/issue-bound kernel: algorithmic bytes are ~1-5 B per spin-step, so the HBM fraction is "
-                        "small by construction; see profiles/ for issue-slot and L2 sector counters"}
+    roofline = W.roofline(H, counts, T, args.steps, per_spin_out, peak, peak_src, mode, args)
 
     line = {"metric": "spin-steps/s", "value": value, "unit": "spin-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": T["dev_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if mode == sw.MODE_FAST else "f32+f64", "data": "synthetic",
-            "config": {"workload": desc, "spins_per_gpu": S_per_gpu, "n_scales": K, "timepoints": cfg.n_timepoints,
-                       "scans": eng.n_dummy_scan + 1, "spin_steps_per_pass": steps_per_pass_rank * world,
-                       "rng": "philox4x32-10, one block per two steps + Box-Muller (SWK_MODE_FAST)" if mode == sw.MODE_FAST else "minstd_rand + erfcinvf (SWK_MODE_COMPAT, reference arithmetic)",
-                       "l2": f"inputs larger than L2 (phantom {5 * ph['n'] ** 3 / 1e9:.2f} GB vs 126 MB)" if ph["n"] >= 600 else "phantom fits in L2; outputs (12.5 GB > L2) rewritten every pass",
-                       "phantom": f"generated on the device by swk_generate_phantom: {gen['n_shapes']} shapes, volume fraction {gen['volume_fraction']:.3f} %, "
-                                  f"voxel fill {gen['kernel_ms']:.2f} ms (bit-identical to the reference's `spinwalk phantom` for this recipe)",
-                       "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums",
-                       **({"zslab": "SWK_ZSLAB=1: z-invariant phantom walked on its [nx][ny] slab (opt-in specialisation; the voxel table is then L1/L2-resident, NOT the default path and not the headline configuration)"} if os.environ.get("SWK_ZSLAB") else {})},
-            "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": args.steps * st["n_launches"],
-            "e2e": e2e, "roofline": roofline, "lost_spins": st_counts["lost"]}
+            "config": {"workload": desc, "spins_per_gpu": S_per_gpu, "n_scales": K, "timepoints": H["cfg"].n_timepoints,
+                       "scans": H["eng"].n_dummy_scan + 1, "spin_steps_per_pass": H["steps_per_pass"] * world,
+                       "rng": "philox4x32-10 (one block per two rounds, shared by all FoV scales of a spin) + Box-Muller (SWK_MODE_FAST)" if mode == sw.MODE_FAST
+                              else "minstd_rand + erfcinvf (SWK_MODE_COMPAT, reference arithmetic)",
+                       "voxel_table": H["table"],
+                       "l2": "per-spin outputs (12.5 GB > L2) rewritten every pass; the voxel table of this z-invariant phantom is its [nx][ny] slab (L1/L2 resident) — "
+                             "`full_table` below is the same workload on the full [nx][ny][nz] table (larger than L2)" if H["slab"] else
+                             f"inputs larger than L2 (voxel table {4 * ph['n'] ** 3 / 1e9:.2f} GB vs 126 MB)" if ph["n"] >= 400 else "phantom fits in L2; outputs rewritten every pass",
+                       "phantom": H["phantom_note"],
+                       "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums"},
+            "clocks": clocks, "wall_ms_per_step": T["wall_ms"] / args.steps, "gpu_launches": args.steps * T["st"]["n_launches"],
+            "e2e": e2e, "roofline": roofline, "lost_spins": counts["lost"]}
 
-    mask2 = fm2 = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload != "c5":  # (C5's 5 GB host phantom: use C2's baseline)
-        mask2, fm2 = eng.get_phantom()  # the baselines below walk the very same voxels
-        try:
-            cb, _, _ = cpu_reference(cfg_kw, ph, mask2, fm2, fov, target_s=15.0)
-            line["cpu_baseline"] = cb
-        except Exception as ex:  # the baseline is a reported extra; never lose the GPU line over it
-            line["cpu_baseline"] = {"value": None, "unit": "spin-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
-    eng.close()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = W.cpu_baseline(H, cfg_kw, ph)
+    W.close(H)
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload not in ("c5", "c4"):
         try:  # the reference's own CUDA kernel on this GPU, for context; never the thing measured above
             torch.cuda.empty_cache()
-            line["reference_cuda"] = reference_cuda(cfg_kw, ph, mask2, fm2, fov, local_rank)
+            mask2, fm2 = H["host_phantom"]
+            line["reference_cuda"] = reference_cuda(cfg_kw, ph, mask2, fm2, H["fov"], local_rank)
         except Exception as ex:
             line["reference_cuda"] = {"value": None, "sample": f"failed: {ex}"}
+    H.pop("host_phantom", None)
+
+    # ---- sub-records (every N): the same engine on the configurations VERDICT r1 asked for, each a bounded, separately timed run
+    if args.workload == "c2" and mode == sw.MODE_FAST and not args.no_extras and not args.spins and not args.scales:
+        for name, fn in (("full_table", W.extra_full_table), ("compat", W.extra_compat), ("scale_groups", W.extra_scale_groups),
+                         ("non_invariant", W.extra_non_invariant), ("north_star", W.extra_north_star)):
+            try:
+                line[name] = fn(peak, peak_src, args)
+            except Exception as ex:  # an extra must never cost the headline line
+                line[name] = {"error": f"{type(ex).__name__}: {ex}"}
+            torch.cuda.empty_cache()
     if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_phantom(ph):
+    """The workload's phantom for the CPU reference arm, WITHOUT a GPU: the recipe through the oracle's restatement of `spinwalk phantom`
+    (bit-identical to the reference's generator and to the product's GPU generator, tests/test_phantom_oracle.py / test_phantom_gpu.py).
+    Cylinder phantoms do not depend on z: one z slice is computed and the caller broadcasts it (full_phantom)."""
+    from oracle import pyphantom as pp
+
+    import subprocess as sp
+
+    fov = (np.float32(ph["fov_um"]) * np.float32(1e-6),) * 3
+    fov = tuple(float(f) for f in fov)
+    try:
+        sp.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True)
+        if ph["kind"] == "spheres":
+            kw = dict(shape=pp.SPHERE, fov_um=ph["fov_um"], resolution=ph["n"], Y=-1.0, radius_um=-20.0, volume_fraction=ph["vf"], seed=ph["seed"])
+            r = pp.reference(omp=True, **kw) if pp.have_ref(omp=True) else pp.oracle(**kw)
+            return r.mask, None, fov
+        r = pp.oracle(zwin=(0, 1), shape=pp.CYLINDER, fov_um=ph["fov_um"], resolution=ph["n"], Y=ph["Y"], radius_um=ph["radius_um"],
+                      volume_fraction=ph["bvf"], orientation_deg=90.0, seed=ph["seed"])
+        return np.ascontiguousarray(r.mask[:, :, 0]), np.ascontiguousarray(r.fieldmap[:, :, 0]), fov
+    except Exception:  # the numpy stand-in of the same recipe (statistically, not bitwise, the reference's shapes)
+        return make_phantom_2d(ph)
+
+
+class Walk:
+    """The walk legs of the bench: one engine per workload, timed passes with the NCCL all-reduce of the sums inside."""
+
+    def __init__(self, sw, torch, dist, dev, rank, world, local_rank):
+        self.sw, self.torch, self.dist, self.dev, self.rank, self.world, self.local_rank = sw, torch, dist, dev, rank, world, local_rank
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def setup(self, name, cfg_kw, ph, spec=None):
+        """engine with the workload's phantom (generated on this rank's device from the reference's own `spinwalk phantom` recipe — bit-identical
+        to the reference's generator, tests/test_phantom_gpu.py — it never visits the host), sequence and this rank's shard of the spins."""
+        from spinwalk_b200 import sharding
+
+        sw, torch = self.sw, self.torch
+        S = cfg_kw["n_spins"]
+        cfg = sw.SimConfig(**dict(cfg_kw, n_spins=S * self.world))  # weak scaling: the global population grows with N
+        eng = sw.Engine(self.local_rank)
+        gen = eng.generate_phantom(spec or phantom_spec(ph))
+        spin_first, n_local = sharding.shard_range(S * self.world, self.rank, self.world)
+        assert n_local == S
+        xyz0_pin = torch.empty((S, 3), dtype=torch.float32, pin_memory=True)
+        xyz0_pin.numpy()[:] = make_positions(S, eng.fov, cfg.seed, spin_first)
+        eng.set_sequence(cfg)
+        eng.set_spins(xyz0_pin.numpy(), None, spin_first)
+        K, E, ns = len(cfg.scales), cfg.n_TE, cfg.n_substrate
+        slab = ph["kind"] != "spheres" and os.environ.get("SWK_NO_ZSLAB") is None
+        return dict(name=name, eng=eng, cfg=cfg, S=S, K=K, E=E, ns=ns, fov=eng.fov, spin_first=spin_first, xyz0_pin=xyz0_pin, slab=slab, n=ph["n"],
+                    sums_d=torch.zeros((K, E, ns, 4), dtype=torch.float64, device=self.dev),
+                    steps_per_pass=S * K * (eng.n_dummy_scan + 1) * cfg.n_timepoints,
+                    table=(f"z slab [nx][ny] of the z-invariant phantom: {4 * ph['n'] ** 2 / 1e6:.2f} MB (default, include/spinwalk_engine.h SWK_RUN_NO_ZSLAB)" if slab
+                           else f"[nx][ny][nz] packed words: {4 * ph['n'] ** 3 / 1e9:.3f} GB" if gen.get("n_shapes") is not None and ph.get("Y", 0) is not None and ph["kind"] != "spheres" or (spec is not None)
+                           else f"[nx][ny][nz] mask bytes: {ph['n'] ** 3 / 1e9:.3f} GB (no field map)"),
+                    phantom_note=f"generated on the device by swk_generate_phantom: {gen['n_shapes']} shapes, volume fraction {gen['volume_fraction']:.3f} %, "
+                                 f"voxel fill {gen['kernel_ms']:.2f} ms (bit-identical to the reference's `spinwalk phantom` for this recipe)")
+
+    def one_pass(self, H, mode, flags, scales=None):
+        from spinwalk_b200 import sharding
+
+        sums = H["sums_d"] if scales is None else H["sums_d"][: len(scales)]
+        st = H["eng"].run_device(scales=scales, mode=mode, flags=flags, d_sums_ptr=sums.data_ptr())
+        sharding.allreduce_sums(sums)  # the one collective of the path: a few KB of per-echo ensemble sums (NCCL)
+        return st
+
+    def counts(self, H, mode, flags, scales=None):
+        """work counters (voxel changes, rejections) of one untimed pass of the STATS kernel variant: the roofline's algorithmic bytes"""
+        return self.one_pass(H, mode, flags | self.sw.RUN_STATS, scales)
+
+    def timed(self, H, mode, flags, steps, warmup, scales=None):
+        torch = self.torch
+        for _ in range(warmup):
+            self.one_pass(H, mode, flags, scales)
+        self.barrier()
+        dev_ms = ker_ms = 0.0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            st = self.one_pass(H, mode, flags, scales)
+            dev_ms += st["device_ms"]
+            ker_ms += st["kernel_ms"]
+        self.barrier()
+        wall_s = time.perf_counter() - t0
+        t = torch.tensor([dev_ms, ker_ms, wall_s * 1e3], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        dev_ms, ker_ms, wall_ms = (float(v) for v in t.tolist())
+        return dict(dev_ms=dev_ms, ker_ms=ker_ms, wall_ms=wall_ms, st=st)
+
+    def e2e(self, H, mode, per_spin_out, steps):
+        """end to end through swk_run with host buffers: H2D of XYZ0 and D2H of M1 / XYZ1 / T / sums inside the timed region"""
+        from spinwalk_b200 import sharding
+
+        torch, eng = self.torch, H["eng"]
+        K, S, E, ns = H["K"], H["S"], H["E"], H["ns"]
+        if per_spin_out:
+            out = (torch.empty((K, S, E, 3), dtype=torch.float32, pin_memory=True), torch.empty((K, S, eng.trj, 3), dtype=torch.float32, pin_memory=True),
+                   torch.empty((K, S, E), dtype=torch.uint8, pin_memory=True))
+            out_np = tuple(o.numpy() for o in out)
+        else:
+            out, out_np = (), None
+        h2d = H["xyz0_pin"].numel() * 4 + K * 4
+        d2h = sum(o.numel() * o.element_size() for o in out) + K * E * ns * 4 * 8
+        x = H["xyz0_pin"].numpy()
+        eng.run(x, None, H["spin_first"], mode=mode, out=out_np, outputs=per_spin_out, stats=False)  # warm
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = eng.run(x, None, H["spin_first"], mode=mode, out=out_np, outputs=per_spin_out, stats=False)
+            if self.world > 1:
+                H["sums_d"].copy_(torch.from_numpy(r["sums"]))
+                sharding.allreduce_sums(H["sums_d"])
+        self.barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(te, op=self.dist.ReduceOp.MAX)
+        del out, out_np
+        return {"value": H["steps_per_pass"] * self.world * steps / float(te.item()), "unit": "spin-steps/s", "h2d_bytes_per_step": h2d * self.world,
+                "d2h_bytes_per_step": d2h * self.world, "ms_per_step": 1e3 * float(te.item()) / steps,
+                "api": "swk_run (C-ABI) with pinned host buffers: XYZ0 in; " + ("M1, XYZ1, T, sums out" if per_spin_out else "sums out")}
+
+    def roofline(self, H, counts, T, steps, per_spin_out, peak, peak_src, mode, args, steps_scale=1.0):
+        sw = self.sw
+        K, E, S = H["K"], H["E"], H["S"]
+        per_pass_bytes = (counts["mask_gathers"] * (4 if H["eng"].has_fieldmap else 1)) * steps_scale + S * K * (24 + ((13 * E + 12) if per_spin_out else 0))
+        ker_ms = T["ker_ms"] / steps
+        achieved = per_pass_bytes / (ker_ms * 1e-3) / 1e9
+        traffic, traffic_src = stamped_traffic(f"{H['name']}:{args.mode}{'' if H['slab'] else ':full'}", S)
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "kernel": "swk::walk_fast_kernel" if mode == sw.MODE_FAST else "swk::walk_compat_kernel",
+                "algorithmic_bytes_per_launch": per_pass_bytes, "kernel_ms_per_launch": ker_ms, "bytes_per_spin_step": per_pass_bytes / H["steps_per_pass"],
+                "attempts_with_voxel_change_per_step": counts["mask_gathers"] * steps_scale / max(1, H["steps_per_pass"]),
+                "rejects_per_step": counts["rejects"] * steps_scale / max(1, H["steps_per_pass"]),
+                "note": "algorithmic bytes (SURVEY §8d): 4 B packed voxel word per attempt whose voxel changed + 24 B in + (13 E + 12) B out per (spin, scale).  "
+                        + ("With the z-slab table the words come from L1/L2: the launch is ISSUE bound (ncu: issue slots, profiles/README.md), so this HBM fraction is small by "
+                           "construction; the gather roofline is measured by `full_table`." if H["slab"] else
+                           "A 4-byte gather costs a 64-byte HBM access, so the byte fraction is small by construction; `gather` compares the walk with the random-gather probe.")}
+
+    def cpu_baseline(self, H, cfg_kw, ph, target_s=15.0):
+        try:
+            mask, fm = H["eng"].get_phantom()  # the baseline walks the very same voxels
+            H["host_phantom"] = (mask, fm)
+            cb, _, _ = cpu_reference(cfg_kw, ph, mask, fm, H["fov"], target_s=target_s)
+            return cb
+        except Exception as ex:  # the baseline is a reported extra; never lose the GPU line over it
+            return {"value": None, "unit": "spin-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+
+    def close(self, H):
+        H["eng"].close()
+        for k in ("xyz0_pin", "sums_d"):
+            H.pop(k, None)
+
+    # ------------------------------------------------------------------ sub-records
+    def gather_roofline(self, H, mode, n_small=10):
+        """the walk against the random-gather probe on the SAME table, on the smallest FoV scales only — there every attempt lands in a voxel far
+        from the last one (sigma >= 4 voxels), so walk gathers and probe gathers are the same kind of access (L2 hits included on both sides)"""
+        small = list(H["cfg"].scales[:n_small])
+        c = self.counts(H, mode, 0, small)
+        t = self.timed(H, mode, 0, 2, 1, small)
+        probe = H["eng"].probe_gather(threads_per_sm=2048, iters=2048)
+        walk = c["mask_gathers"] / (t["ker_ms"] / 2 * 1e-3)
+        return {"scales": [small[0], small[-1]], "walk_gathers_per_s": walk, "probe_gathers_per_s": probe["gathers_per_s"], "table_bytes": probe["table_bytes"],
+                "frac": walk / probe["gathers_per_s"], "kernel_ms": t["ker_ms"] / 2,
+                "note": "probe = swk_probe_gather: dependent random 4-byte gathers over the same voxel table with the walk's load instruction and nothing else "
+                        "(HBM row-activation bound, DESIGN.md §5); walk = attempts whose voxel changed (STATS kernel variant) / kernel time of the same scales"}
+
+    def extra_full_table(self, peak, peak_src, args):
+        """the headline workload on the FULL [nx][ny][nz] voxel table (SWK_RUN_NO_ZSLAB): what a phantom without an invariant axis costs, and the
+        configuration the gather roofline applies to"""
+        sw = self.sw
+        cfg_kw, ph, desc = workload("c2", None, None)
+        H = self.setup("c2", cfg_kw, ph)
+        H["slab"] = False
+        fl = sw.OUT_ALL | sw.RUN_NO_ZSLAB
+        counts = self.counts(H, sw.MODE_FAST, fl)
+        T = self.timed(H, sw.MODE_FAST, fl, 2, 1)
+        rec = {"value": H["steps_per_pass"] * self.world * 2 / (T["dev_ms"] * 1e-3), "unit": "spin-steps/s", "ms_per_step": T["dev_ms"] / 2, "steps": 2, "warmup": 1,
+               "config": {"workload": desc + "; full voxel table (864 MB, HBM resident)", "spins_per_gpu": H["S"]},
+               "roofline": self.roofline(H, counts, T, 2, True, peak, peak_src, sw.MODE_FAST, args)}
+        fl0 = sw.RUN_NO_ZSLAB
+        H2 = dict(H)
+        small = list(H["cfg"].scales[:10])
+        c = self.one_pass(H2, sw.MODE_FAST, fl0 | sw.RUN_STATS, small)
+        t = self.timed(H2, sw.MODE_FAST, fl0, 2, 1, small)
+        probe = H["eng"].probe_gather(threads_per_sm=2048, iters=2048)
+        walk = c["mask_gathers"] / (t["ker_ms"] / 2 * 1e-3)
+        rec["roofline"]["gather"] = {"scales": [small[0], small[-1]], "walk_gathers_per_s": walk, "probe_gathers_per_s": probe["gathers_per_s"],
+                                     "table_bytes": probe["table_bytes"], "frac": walk / probe["gathers_per_s"], "kernel_ms": t["ker_ms"] / 2,
+                                     "note": "the walk against the random-gather probe on the SAME table, on the 10 smallest FoV scales only: there every attempt lands in a "
+                                             "voxel far from the last one (sigma >= 4 voxels), so both count the same kind of access (L2 hits included on both sides).  "
+                                             "probe = swk_probe_gather: dependent random 4-byte gathers with the walk's load instruction and nothing else (HBM row-activation "
+                                             "bound, DESIGN.md §5); walk = attempts whose voxel changed (STATS kernel variant) / kernel time"}
+        self.close(H)
+        return rec
+
+    def extra_compat(self, peak, peak_src, args):
+        """SWK_MODE_COMPAT — the reference's own arithmetic (minstd + erfcinvf, FP64 positions), bit-exact against its cu_sim — on a 2e6-spin sample"""
+        sw = self.sw
+        cfg_kw, ph, desc = workload("c2", 2_000_000, None)
+        H = self.setup("c2", cfg_kw, ph)
+        T = self.timed(H, sw.MODE_COMPAT, sw.OUT_ALL, 2, 1)
+        rec = {"value": H["steps_per_pass"] * self.world * 2 / (T["dev_ms"] * 1e-3), "unit": "spin-steps/s", "ms_per_step": T["dev_ms"] / 2, "steps": 2, "warmup": 1,
+               "dtype": "f32+f64", "config": {"workload": desc.replace("1e7 spins", "2e6 of the 1e7 spins") + "; SWK_MODE_COMPAT (bit-exact T / XYZ1 vs the reference's cu_sim, "
+                                              "tests/test_engine_gpu.py); mask byte + FP32 field from the full arrays", "spins_per_gpu": H["S"]}}
+        self.close(H)
+        return rec
+
+    def extra_scale_groups(self, peak, peak_src, args):
+        """kernel time of the headline workload per group of 10 consecutive FoV scales (1e7 spins each): where the pass spends its time"""
+        sw = self.sw
+        cfg_kw, ph, desc = workload("c2", None, None)
+        H = self.setup("c2", cfg_kw, ph)
+        out = []
+        sc = list(H["cfg"].scales)
+        for g in range(0, len(sc), 10):
+            part = sc[g:g + 10]
+            c = self.counts(H, sw.MODE_FAST, 0, part)
+            t = self.timed(H, sw.MODE_FAST, 0, 1, 1, part)
+            n = H["S"] * len(part) * H["cfg"].n_timepoints
+            out.append({"scales": [part[0], part[-1]], "kernel_ms": t["ker_ms"], "spin_steps_per_s": n * self.world / (t["dev_ms"] * 1e-3),
+                        "attempts_per_step": 1.0 + c["rejects"] / max(1, c["steps"]), "voxel_changes_per_step": c["mask_gathers"] / max(1, c["steps"])})
+        self.close(H)
+        return out
+
+    def extra_non_invariant(self, peak, peak_src, args):
+        """a phantom WITHOUT an invariant axis: SE BOLD on 400^3 random spheres with their dipole field map (`phantom -s -r -20 -v 30 -y 0.78`), full packed table (256 MB > L2)"""
+        sw = self.sw
+        from spinwalk_b200 import phantom_gen as pg
+
+        cfg_kw, _, _ = workload("c2", 2_000_000, None)
+        ph = dict(kind="spheres", n=400, fov_um=400.0, vf=30.0, seed=0, Y=0.78)
+        spec = pg.PhantomSpec(shape=pg.SHAPE_SPHERE, fov_um=400.0, resolution=400, oxy_level=0.78, radius_um=-20.0, volume_fraction=30.0, seed=0)
+        H = self.setup("c2s", cfg_kw, ph, spec=spec)
+        H["slab"] = False
+        counts = self.counts(H, sw.MODE_FAST, sw.OUT_ALL)
+        T = self.timed(H, sw.MODE_FAST, sw.OUT_ALL, 2, 1)
+        rec = {"value": H["steps_per_pass"] * self.world * 2 / (T["dev_ms"] * 1e-3), "unit": "spin-steps/s", "ms_per_step": T["dev_ms"] / 2, "steps": 2, "warmup": 1,
+               "config": {"workload": "SE BOLD (config/se.ini) on `phantom -s -r -20 -v 30 -y 0.78 -f 400 -z 400 -e 0`: 400^3 random spheres + dipole field map (no invariant axis), "
+                                      "2e6 spins x 50 FoV scales", "spins_per_gpu": H["S"], "phantom": H["phantom_note"]},
+               "roofline": self.roofline(H, counts, T, 2, True, peak, peak_src, sw.MODE_FAST, args), "lost_spins": counts["lost"]}
+        rec["roofline"]["gather"] = self.gather_roofline(H, sw.MODE_FAST)
+        self.close(H)
+        return rec
+
+    def extra_north_star(self, peak, peak_src, args):
+        """BASELINE.json configs[4] / north_star: 1000^3 BOLD phantom, 1.25e8 spins per GPU (1e9 over 8), 50 FoV scales, ensemble sums only, NCCL all-reduce"""
+        sw = self.sw
+        cfg_kw, ph, desc = workload("c5", None, None)
+        H = self.setup("c5", cfg_kw, ph)
+        T = self.timed(H, sw.MODE_FAST, 0, 2, 1)
+        rec = {"value": H["steps_per_pass"] * self.world * 2 / (T["dev_ms"] * 1e-3), "unit": "spin-steps/s", "n_gpus": self.world, "ms_per_step": T["dev_ms"] / 2, "steps": 2,
+               "warmup": 1, "scaling": "weak", "config": {"workload": desc, "spins_per_gpu": H["S"], "spins_total": H["S"] * self.world, "voxel_table": H["table"],
+                                                            "phantom": H["phantom_note"]},
+               "gpu_launches": 2 * T["st"]["n_launches"]}
+        # the same phantom on its full 4 GB voxel table, 2.5e7 of the spins: the gather-roofline configuration of the north star
+        S_small = 25_000_000
+        H["eng"].set_spins(H["xyz0_pin"].numpy()[:S_small], None, H["spin_first"])
+        Hs = dict(H, S=S_small, slab=False, steps_per_pass=S_small * H["K"] * H["cfg"].n_timepoints)
+        fl = sw.RUN_NO_ZSLAB
+        counts = self.counts(Hs, sw.MODE_FAST, fl)
+        Tf = self.timed(Hs, sw.MODE_FAST, fl, 1, 1)
+        ft = {"value": Hs["steps_per_pass"] * self.world / (Tf["dev_ms"] * 1e-3), "unit": "spin-steps/s", "ms_per_step": Tf["dev_ms"], "steps": 1, "warmup": 1,
+              "config": {"workload": "the same phantom on its full [nx][ny][nz] table (4 GB, SWK_RUN_NO_ZSLAB), 2.5e7 spins per GPU x 50 FoV scales, sums only", "spins_per_gpu": S_small},
+              "roofline": self.roofline(Hs, counts, Tf, 1, False, peak, peak_src, sw.MODE_FAST, args)}
+        small = list(H["cfg"].scales[:10])
+        c = self.one_pass(Hs, sw.MODE_FAST, fl | sw.RUN_STATS, small)
+        t = self.timed(Hs, sw.MODE_FAST, fl, 1, 1, small)
+        probe = H["eng"].probe_gather(threads_per_sm=2048, iters=2048)
+        walk = c["mask_gathers"] / (t["ker_ms"] * 1e-3)
+        ft["roofline"]["gather"] = {"scales": [small[0], small[-1]], "walk_gathers_per_s": walk, "probe_gathers_per_s": probe["gathers_per_s"], "table_bytes": probe["table_bytes"],
+                                    "frac": walk / probe["gathers_per_s"], "kernel_ms": t["ker_ms"],
+                                    "note": "walk vs random-gather probe on the same 4 GB table, 10 smallest FoV scales (see full_table.roofline.gather.note)"}
+        rec["full_table"] = ft
+        if self.rank == 0 and self.world == 1 and not args.no_cpu_baseline:
+            rec["cpu_baseline"] = self.cpu_baseline(H, cfg_kw, ph, target_s=10.0)
+            H.pop("host_phantom", None)
+        self.close(H)
+        return rec
+
+
+def source_stamp():
+    """identity of the kernels a capture belongs to: SHA-256 over the CUDA sources (they travel with every snapshot)"""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "spinwalk_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.startswith(("walk_", "engine")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def stamped_traffic(key, spins_per_gpu):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json, written by scripts/make_traffic.py) — only when the capture was
+    taken on THESE kernel sources; a stale capture is refused, not silently reused."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, "no capture (profiles/traffic.json missing)"
+    ent = tj.get(key)
+    if not ent:
+        return None, f"no capture for {key}"
+    if ent.get("kernel_stamp") != source_stamp():
+        return None, f"stale capture refused: taken on kernel sources {ent.get('kernel_stamp')}, this build is {source_stamp()}"
+    return ent["dram_bytes_per_launch"] * (spins_per_gpu / ent["spins_per_gpu"]), ent["source"]
 
 
 if __name__ == "__main__":

@@ -4,9 +4,11 @@
 //   spinwalk phantom -c|-s|-t -f FOV -z RES -o FILE [-r -n -v -d -y -e]   numerical phantom, voxel fill on the GPU (:58-72)
 //   spinwalk config  -s SEQ -p PHANTOM... -e TE -t DT -o FILE     GRE / SE / bSSFP configuration (:73-78)
 //   spinwalk dwi     -b B... -v X Y Z -d START δ Δ -c CONFIG      PGSE gradient table into a config (:80-84)
-// Option names, defaults and mandatory flags follow the reference.  This build has no CPU path: `sim -p` is accepted and refused
-// with a clear message.  Extensions: -d takes a comma-separated list (spins sharded over
-// several GPUs), --compat selects the reference-arithmetic kernel, --sums adds the ensemble sums to the output file, -q is quiet.
+// Option names, defaults and mandatory flags follow the reference.  This build has no CPU path: `sim -p` is accepted with a warning and
+// the simulation runs on the GPU.  Extensions: -d takes a comma-separated list (spins sharded over several GPUs, phantom
+// replicated), --compat selects the reference-arithmetic kernel, --sums adds the ensemble sums to the output file, --sums-only writes
+// nothing but the sums (no per-spin arrays on the host or the device: what makes 1e9-spin runs possible), --device-positions draws the
+// default start positions on the GPU, -q is quiet.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,8 +28,17 @@ void usage()
             "spinwalk (B200 engine)\n"
             "Usage: spinwalk [-g] [-l LOG] SUBCOMMAND ...\n"
             "  sim      -c,--configs FILE...   config. files as many as you want\n"
-            "           -p,--use_cpu           not available: this engine has no CPU path\n"
-            "           -d,--device N[,M...]   select GPU device(s); [--compat] [--sums] [--zslab] [-q]\n"
+            "           -p,--use_cpu           accepted with a warning: this engine has no CPU path, the run uses the GPU\n"
+            "           -d,--device N[,M...]   select GPU device(s): spins are sharded over the listed devices\n"
+            "           --compat               the reference CUDA build's arithmetic (minstd_rand + erfcinvf, FP64 positions): per-spin M / XYZ / T\n"
+            "                                  equal the reference's bit for bit.  DEFAULT is the fast path (Philox + Box-Muller, fixed-point\n"
+            "                                  positions, 20-bit field samples): another random stream, results agree with the reference within\n"
+            "                                  Monte-Carlo error, not spin by spin; a spin whose step exceeds both FoV walls stays instead of being lost.\n"
+            "                                  The output file records which one ran (datasets swk_mode: 0 compat / 1 fast, swk_seed).\n"
+            "           --sums                 add dataset sums [scales, echoes, substrates, (sum Mx, sum My, sum Mz, count)]\n"
+            "           --sums-only            write only sums / scales / TE: no per-spin arrays (needed beyond ~1e8 spins)\n"
+            "           --device-positions     default start positions drawn on the GPU (Philox) instead of std::mt19937 on the host\n"
+            "           --full-table           keep the [nx][ny][nz] voxel table even when the phantom does not depend on z;  -q quiet\n"
             "  phantom  -c,--cylinder | -s,--sphere | -t,--two_pools | -p,--ply -i,--ply_file MESH.ply\n"
             "           -r,--radius [50]  -n,--orientation [90]  -v,--volume_fraction [4]  -f,--fov (required)  -z,--resolution (required)\n"
             "           -d,--dchi [0.11e-6]  -y,--oxy_level [0.75]  -e,--seed [-1]  -o,--output (required)  [--device N]\n"
@@ -234,14 +245,21 @@ int run_sim(Args &a)
         if (o == "-p" || o == "--use_cpu") use_cpu = true;
         else if (o == "--compat") opt.compat = true;
         else if (o == "--sums") opt.write_sums = true;
-        else if (o == "--zslab") setenv("SWK_ZSLAB", "1", 1); // opt-in z-slab voxel table (include/spinwalk_engine.h SWK_RUN_ZSLAB)
+        else if (o == "--sums-only") opt.write_sums = opt.sums_only = true;
+        else if (o == "--device-positions") opt.device_positions = true;
+        else if (o == "--full-table") setenv("SWK_NO_ZSLAB", "1", 1); // include/spinwalk_engine.h SWK_RUN_NO_ZSLAB
+        else if (o == "--zslab") {} // round 1's opt-in: the z-slab table is the default now
         else if (o == "-q") opt.quiet = true;
         else if (o == "-d" || o == "--device") {
             if (!a.one(v)) return fail_usage("--device: a number is required");
             opt.devices.clear();
             for (size_t p = 0; p <= v.size();) {
                 const size_t q = std::min(v.find(',', p), v.size());
-                opt.devices.push_back(atoi(v.substr(p, q - p).c_str()));
+                const std::string tok = v.substr(p, q - p);
+                char *end = nullptr;
+                const long id = strtol(tok.c_str(), &end, 10);
+                if (tok.empty() || *end != '\0' || id < 0 || id > 1023) return fail_usage("--device: not a device id: '" + tok + "'");
+                opt.devices.push_back((int)id);
                 p = q + 1;
             }
         } else if (o == "-c" || o == "--configs") {
@@ -252,7 +270,7 @@ int run_sim(Args &a)
     if (configs.empty()) return fail_usage("--configs is required");
     for (const auto &c : configs)
         if (!std::filesystem::exists(c)) return fail_usage("--configs: File does not exist: " + c);
-    if (use_cpu) { fprintf(stderr, "-p/--use_cpu: this engine has no CPU path (by design); run without -p\n"); return 1; }
+    if (use_cpu) fprintf(stderr, "warning: -p/--use_cpu ignored: this engine has no CPU path (by design); the simulation runs on the GPU\n");
     std::string err;
     if (!swk_host::run_sim(configs, opt, err)) {
         fprintf(stderr, "Simulation failed. See the log file\n%s\n", err.c_str()); // spinwalk.cpp:131-134

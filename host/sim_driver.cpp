@@ -134,37 +134,42 @@ bool run_one(const std::string &config_file, const SimOptions &opt, std::string 
     T.gradZ_mTm = cfg.gradientZ_mTm.data(); T.n_gradZ = (uint32_t)cfg.gradientZ_mTm.size();
     T.gradient_tp = cfg.gradient_us.data(); T.n_gradient = (uint32_t)cfg.gradient_us.size();
 
-    // ---- engines: one per device, spins sharded by contiguous id range ----
-    const size_t G = opt.devices.size();
+    // ---- engines: one per device, spins sharded by contiguous id range (never more engines than spins: no empty shard) ----
+    const size_t S = cfg.n_spins, K = cfg.scales.size(), E = cfg.TE_us.size(), ns = cfg.n_substrate;
+    const size_t G = std::min<size_t>(opt.devices.size(), S);
     EngineSet es;
-    for (int dev : opt.devices) {
+    for (size_t g = 0; g < G; g++) {
         swk_engine *e = nullptr;
-        if (swk_create(dev, &e) != SWK_OK) { err = swk_last_error(nullptr); return false; }
+        if (swk_create(opt.devices[g], &e) != SWK_OK) { err = swk_last_error(nullptr); return false; }
         es.e.push_back(e);
         if (swk_set_sequence(e, &P, &T) != SWK_OK) { err = swk_last_error(e); return false; }
     }
 
-    // ---- host arrays, reference layouts (monte_carlo.cu:61-70) ----
-    const size_t S = cfg.n_spins, K = cfg.scales.size(), E = cfg.TE_us.size(), ns = cfg.n_substrate;
+    // ---- host arrays, reference layouts (monte_carlo.cu:61-70); none with --sums-only ----
     const size_t trj = cfg.record_trajectory ? (size_t)P.n_timepoints * (size_t)(P.n_dummy_scan + 1) : 1;
+    const bool per_spin = !opt.sums_only;
     Pinned M1, XYZ1, Tt;
-    if (!M1.alloc(K * S * E * 3 * sizeof(float)) || !XYZ1.alloc(K * S * trj * 3 * sizeof(float)) || !Tt.alloc(K * S * E)) {
-        err = "not enough host memory for the outputs";
+    if (per_spin && (!M1.alloc(K * S * E * 3 * sizeof(float)) || !XYZ1.alloc(K * S * trj * 3 * sizeof(float)) || !Tt.alloc(K * S * E))) {
+        err = "not enough host memory for the outputs (--sums-only writes the ensemble sums without per-spin arrays)";
         return false;
     }
-    std::vector<float> xyz0(S * 3), m0(S * 3);
+    std::vector<float> xyz0, m0(0);
     std::vector<double> sums(K * E * ns * 4), part(K * E * ns * 4);
 
     for (size_t ip = 0; ip < cfg.phantom.size(); ip++) {
         if (!opt.quiet) fprintf(stderr, "Simulating phantom: %s\n", cfg.phantom[ip].c_str());
         Phantom ph;
         if (!read_phantom(cfg.phantom[ip], ph, err)) return false;
-        if (!init_positions(cfg.xyz0[ip], P.seed, ph.fov, xyz0, err)) return false;
+        const bool dev_pos = opt.device_positions && cfg.xyz0[ip].empty(); // an XYZ0 file always wins
+        if (!dev_pos) {
+            xyz0.resize(S * 3);
+            if (!init_positions(cfg.xyz0[ip], P.seed, ph.fov, xyz0, err)) return false;
+        }
         if (!cfg.m0[ip].empty()) { // the reference reads the file (size check) and then overwrites M0 with (0,0,1) anyway (monte_carlo.cu:155-166)
             h5::Reader r;
             h5::DatasetInfo di;
             if (!r.open(cfg.m0[ip]) || !r.info("M", di)) { err = r.error(); return false; }
-            if (di.count() != m0.size()) { err = "dataset \"M\" has different size " + std::to_string(di.count()) + " vs " + std::to_string(m0.size()); return false; }
+            if (di.count() != S * 3) { err = "dataset \"M\" has different size " + std::to_string(di.count()) + " vs " + std::to_string(S * 3); return false; }
         }
         auto t_sim = std::chrono::steady_clock::now();
         std::fill(sums.begin(), sums.end(), 0.0);
@@ -176,9 +181,9 @@ bool run_one(const std::string &config_file, const SimOptions &opt, std::string 
             const float fov[3] = {ph.fov[0], ph.fov[1], ph.fov[2]};
             if (swk_set_phantom(e, ph.mask.data(), ph.fieldmap.empty() ? nullptr : ph.fieldmap.data(), ph.dims, fov, 0) != SWK_OK ||
                 swk_set_host_rows(e, S, first) != SWK_OK ||
-                swk_run(e, xyz0.data() + 3 * first, nullptr /* M0 = (0,0,1) */, (uint32_t)first, (uint32_t)(last - first), cfg.scales.data(), (uint32_t)K,
-                        cfg.scale_type, opt.compat ? SWK_MODE_COMPAT : SWK_MODE_FAST, static_cast<float *>(M1.p), static_cast<float *>(XYZ1.p),
-                        static_cast<uint8_t *>(Tt.p), parts[g].data(), nullptr) != SWK_OK)
+                swk_run(e, dev_pos ? nullptr : xyz0.data() + 3 * first, nullptr /* M0 = (0,0,1) */, (uint32_t)first, (uint32_t)(last - first), cfg.scales.data(),
+                        (uint32_t)K, cfg.scale_type, opt.compat ? SWK_MODE_COMPAT : SWK_MODE_FAST, per_spin ? static_cast<float *>(M1.p) : nullptr,
+                        per_spin ? static_cast<float *>(XYZ1.p) : nullptr, per_spin ? static_cast<uint8_t *>(Tt.p) : nullptr, parts[g].data(), nullptr) != SWK_OK)
                 errs[g] = swk_last_error(e);
         };
         if (G == 1) work(0);
@@ -200,14 +205,19 @@ bool run_one(const std::string &config_file, const SimOptions &opt, std::string 
         std::filesystem::remove(out, ec);
         std::filesystem::create_directories(std::filesystem::absolute(out).parent_path(), ec);
         h5::Writer w(out);
-        w.add("M", {K, S, E, 3}, h5::DType::F32, M1.p);
-        w.add("XYZ", {K, S, trj, 3}, h5::DType::F32, XYZ1.p);
-        w.add("T", {K, S, E, 1}, h5::DType::U8, Tt.p);
+        if (per_spin) {
+            w.add("M", {K, S, E, 3}, h5::DType::F32, M1.p);
+            w.add("XYZ", {K, S, trj, 3}, h5::DType::F32, XYZ1.p);
+            w.add("T", {K, S, E, 1}, h5::DType::U8, Tt.p);
+        }
         w.add("scales", {K, 1, 1, 1}, cfg.scales);
         std::vector<float> te_s;
         for (int32_t tp : cfg.TE_us) te_s.push_back(tp * cfg.timestep_us * 1e-6); // timepoints back to seconds (monte_carlo.cu:192-193)
         w.add("TE", {E, 1, 1, 1}, te_s);
         if (opt.write_sums) w.add("sums", {K, E, ns, 4}, sums);
+        // which arithmetic produced the file (the reference has one; this engine has two): 0 = --compat (the reference's, spin by spin), 1 = fast
+        w.add("swk_mode", {1}, std::vector<uint8_t>{(uint8_t)(opt.compat ? SWK_MODE_COMPAT : SWK_MODE_FAST)});
+        w.add("swk_seed", {1}, std::vector<uint64_t>{(uint64_t)P.seed});
         if (!w.close()) { err = w.error(); return false; }
         if (!opt.quiet) fprintf(stderr, "Saved %s\n", out.c_str());
     }

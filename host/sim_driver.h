@@ -14,6 +14,8 @@ struct SimOptions {
     std::vector<int> devices = {0}; // -d: one id like the reference, or a comma-separated list (spins sharded, phantom replicated)
     bool compat = false;            // --compat: the reference CUDA build's arithmetic (bit-exact walks) instead of the fast path
     bool write_sums = false;        // --sums: add the per-(scale, echo, substrate) ensemble sums as dataset "sums"
+    bool sums_only = false;         // --sums-only: no per-spin arrays at all (host or device); the output holds sums / scales / TE
+    bool device_positions = false;  // --device-positions: default XYZ0 drawn on the device (swk_set_spins(NULL)) instead of std::mt19937 on the host
     bool quiet = false;
 };
 

@@ -52,7 +52,7 @@ struct swk_engine {
     cudaStream_t cstream[2] = {nullptr, nullptr}; // pipelined host runs: slices alternate between two compute streams
     cudaStream_t dstream = nullptr;               // ... and their results are downloaded on this one
     std::vector<cudaEvent_t> ev_slice;
-    cudaEvent_t evA = nullptr, ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evA = nullptr, ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int sm_count = 0;
     size_t smem_optin = 0;
@@ -415,6 +415,8 @@ void swk_destroy(swk_engine *e)
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     for (cudaEvent_t ev : e->ev_slice) cudaEventDestroy(ev);
     for (cudaStream_t st : {e->cstream[0], e->cstream[1], e->dstream})
         if (st) cudaStreamDestroy(st);
@@ -887,18 +889,28 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     if (mode == SWK_MODE_FAST && std::max(A.nx, std::max(A.ny, A.nz)) > (1u << 20)) return fail(e, SWK_ERR_INVALID, "SWK_MODE_FAST: more than 2^20 voxels along one axis");
 
     // ---- kernel variants and their shared memory ----
-    // COMPAT: [tables] [block sums].  FAST: [tables] [block sums x scales of the block] [scale constants] [normals, SHARED variant].
-    walk_fn kern = nullptr, kern_private = nullptr; // FAST: `kern` is the variant of a launch that starts at scan 0, `kern_private` the one of resumed legs
-    size_t smem = 0, smem_private = 0;
-    unsigned block = kBlock;
+    // COMPAT: [tables] [block sums].  FAST: [tables] [block sums x scales of the block] [scale constants] [event state] [normals, SHARED variant].
+    // A run is cut into `parts`: launches over contiguous scale ranges, each with its own kernel variant.
+    struct Part {
+        uint32_t k_lo, k_hi, group, n_groups;
+        unsigned block;
+        bool shared;
+        size_t fixed, smem;
+        walk_fn kern;
+    };
+    std::vector<Part> parts;
+    walk_fn kern_private = nullptr; // FAST: the variant of legs resumed after a re-binning pause (walkers resume at their own rounds)
+    size_t smem_private = 0;
     const size_t bsum_bytes = A.sums_fx ? E * ns * 4 * sizeof(long long) : 0;
-    bool shared_variant = false;
     if (mode == SWK_MODE_COMPAT) {
         if (bsum_bytes > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
         A.blob_in_smem = (e->L.bytes + bsum_bytes <= smem_cap) ? 1 : 0;
-        smem = (A.blob_in_smem ? e->L.bytes : 0) + bsum_bytes;
-        kern = stats_on ? walk_compat_kernel<true> : walk_compat_kernel<false>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        Part p{};
+        p.k_lo = 0; p.k_hi = n_scales; p.block = kBlock;
+        p.smem = (A.blob_in_smem ? e->L.bytes : 0) + bsum_bytes;
+        p.kern = stats_on ? walk_compat_kernel<true> : walk_compat_kernel<false>;
+        CK(cudaFuncSetAttribute(p.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        parts.push_back(p);
     } else {
         std::vector<uint8_t> tab;
         uint32_t stride = 0;
@@ -916,37 +928,107 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         }
         const size_t fixed_private = ((bsum_bytes + 15) & ~size_t(15)) + stride + (size_t)ES_FIELDS * 4 * kBlock;
         if (fixed_private > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
-        // SHARED variant (walk_fast.cuh): 32 spins x G scales per block share the spins' normals.  Needs >= 2 scales and one spin order for all scales.
-        uint32_t G = (n_scales >= 2 && !(flags & SWK_RUN_NO_SHARE) && getenv("SWK_NO_SHARE") == nullptr) ? shared_group(n_scales) : 1u;
-        if (const char *ev = getenv("SWK_GROUP")) G = std::max(1, std::min(atoi(ev), (int)std::min<uint32_t>(n_scales, SWK_FAST_SHARED_MAXT / 32))); // tuning knob
+        // SHARED variant (walk_fast.cuh): 32 spins x G scales per block share the spins' normals: ~45 instead of ~90 instructions per attempt
+        // where the launch is issue bound.  Where every attempt fetches a voxel far from the last one (step sigma above ~1 voxel: the small FoV
+        // scales) the walk is bound by the gather pipeline instead, the lockstep of a block's scales only costs, and the PRIVATE variant is
+        // faster (measured on C2, profiles/README.md).  A run is therefore cut into at most two launches over contiguous scale ranges.
         const size_t nbuf_bytes = 2 * kBatch * 32 * sizeof(float4);
         auto shared_bytes = [&](uint32_t g) { return ((bsum_bytes * g + 15) & ~size_t(15)) + (size_t)stride * g + (size_t)ES_FIELDS * 4 * 32 * g + nbuf_bytes; };
-        while (G > 1 && shared_bytes(G) > smem_cap) G--; // (many echoes x substrates: fewer scales per block)
-        const size_t fixed_shared = shared_bytes(G);
-        shared_variant = G >= 2;
-        A.blob_in_smem = (e->L.bytes + std::max(fixed_private, shared_variant ? fixed_shared : 0) <= smem_cap) ? 1 : 0;
-        smem_private = (A.blob_in_smem ? e->L.bytes : 0) + fixed_private;
-        kern_private = pick_fast<false>(vox, gruns, record, stats_on);
-        CK(cudaFuncSetAttribute(kern_private, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        if (shared_variant) {
-            A.group = G;
-            A.n_groups = (n_scales + G - 1) / G;
-            block = 32 * G;
-            smem = (A.blob_in_smem ? e->L.bytes : 0) + fixed_shared;
-            kern = pick_fast<true>(vox, gruns, record, stats_on);
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        } else {
-            kern = kern_private;
-            smem = smem_private;
+        double sig_thr = 1.25;
+        if (const char *ev = getenv("SWK_SHARE_SIGMA")) sig_thr = atof(ev); // tuning knob
+        const bool share_off = (flags & SWK_RUN_NO_SHARE) || getenv("SWK_NO_SHARE") != nullptr;
+        std::vector<char> want_shared(n_scales, 0);
+        {
+            const double *sig = reinterpret_cast<const double *>(e->blob_h.data() + e->L.sigma);
+            for (uint32_t k = 0; k < n_scales; k++) {
+                double sv = 0.;
+                for (uint32_t sub = 0; sub < ns; sub++)
+                    for (int i = 0; i < 3; i++) sv = std::max(sv, sig[sub] * (double)e->dims[i] / ((double)e->fov[i] * (scale_type == SWK_SCALE_FOV ? (double)scales[k] : 1.)));
+                want_shared[k] = !share_off && sv <= sig_thr;
+            }
         }
+        // [0, cut) one way and [cut, K) the other when the scales are ordered that way (the default list ascends); a mixed order is decided by the majority
+        uint32_t cut = 0;
+        while (cut < n_scales && want_shared[cut] == want_shared[0]) cut++;
+        bool two = cut < n_scales;
+        for (uint32_t k = cut; two && k < n_scales; k++) two = want_shared[k] == want_shared[cut];
+        if (cut < n_scales && !two) {
+            uint32_t n_sh = 0;
+            for (uint32_t k = 0; k < n_scales; k++) n_sh += want_shared[k];
+            std::fill(want_shared.begin(), want_shared.end(), (char)(2 * n_sh >= n_scales));
+            cut = n_scales;
+        }
+        A.blob_in_smem = 1;
+        auto add_part = [&](uint32_t k_lo, uint32_t k_hi, bool sh) {
+            Part p{};
+            p.k_lo = k_lo; p.k_hi = k_hi;
+            uint32_t G = 1;
+            if (sh) {
+                G = shared_group(k_hi - k_lo);
+                if (const char *ev = getenv("SWK_GROUP")) G = (uint32_t)std::max(1, std::min(atoi(ev), (int)std::min<uint32_t>(k_hi - k_lo, SWK_FAST_SHARED_MAXT / 32))); // tuning knob
+                while (G > 1 && shared_bytes(G) > smem_cap) G--; // (many echoes x substrates: fewer scales per block)
+                if (G < 4) G = 1;                                 // too few walkers per generation of normals to pay for the block barrier
+            }
+            p.shared = G >= 2;
+            p.group = p.shared ? G : 0;
+            p.n_groups = p.shared ? (k_hi - k_lo + G - 1) / G : 0;
+            p.block = p.shared ? 32 * G : (unsigned)kBlock;
+            p.fixed = p.shared ? shared_bytes(G) : fixed_private;
+            p.kern = p.shared ? pick_fast<true>(vox, gruns, record, stats_on) : pick_fast<false>(vox, gruns, record, stats_on);
+            if (e->L.bytes + p.fixed > smem_cap) A.blob_in_smem = 0;
+            parts.push_back(p);
+        };
+        add_part(0, cut, want_shared[0] != 0);
+        if (cut < n_scales) add_part(cut, n_scales, want_shared[cut] != 0);
+        if (parts.size() == 2 && !parts[0].shared && !parts[1].shared) { // (e.g. too few scales on the shared side)
+            parts[0].k_hi = n_scales;
+            parts.pop_back();
+        }
+        for (Part &p : parts) {
+            p.smem = (A.blob_in_smem ? e->L.bytes : 0) + p.fixed;
+            CK(cudaFuncSetAttribute(p.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        }
+        kern_private = pick_fast<false>(vox, gruns, record, stats_on);
+        smem_private = (A.blob_in_smem ? e->L.bytes : 0) + fixed_private;
+        CK(cudaFuncSetAttribute(kern_private, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
     }
-    // blocks of a launch over thread slots [j_first, j_end)
-    auto grid_of = [&](uint32_t j0, uint32_t j1, bool shared) -> uint64_t {
-        const uint64_t n = j1 - j0;
-        return shared ? ((n + 31) / 32) * A.n_groups : ((n + kBlock - 1) / kBlock) * K;
+    // one walk over thread slots [A.j_first, A.j_end): the launches of `parts` (with `fork`, the second part runs beside the first on a second stream)
+    uint32_t walk_launches = 0;
+    auto launch_walk = [&](cudaStream_t st, bool fork, bool resumed) -> int {
+        const uint64_t n = A.j_end - A.j_first;
+        if (resumed) { // FAST legs after a re-binning pause: every walker resumes at its own round
+            A.k_lo = 0; A.k_hi = n_scales; A.group = 0; A.n_groups = 0;
+            const uint64_t grid = ((n + kBlock - 1) / kBlock) * K;
+            if (grid > 0x7fffffffull) return fail(e, SWK_ERR_INVALID, "too many spins x scales for one launch");
+            kern_private<<<(unsigned)grid, kBlock, smem_private, st>>>(A);
+            CK(cudaGetLastError());
+            walk_launches++;
+            return SWK_OK;
+        }
+        for (size_t ip = 0; ip < parts.size(); ip++) {
+            const Part &p = parts[ip];
+            A.k_lo = p.k_lo; A.k_hi = p.k_hi; A.group = p.group; A.n_groups = p.n_groups;
+            const uint64_t grid = p.shared ? ((n + 31) / 32) * p.n_groups : ((n + kBlock - 1) / kBlock) * (p.k_hi - p.k_lo);
+            if (grid > 0x7fffffffull) return fail(e, SWK_ERR_INVALID, "too many spins x scales for one launch");
+            cudaStream_t s2 = st;
+            if (fork && ip == 1) { // the second range beside the first
+                if (!e->cstream[0]) CK(cudaStreamCreateWithFlags(&e->cstream[0], cudaStreamNonBlocking));
+                if (!e->ev_fork) CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+                if (!e->ev_join) CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+                s2 = e->cstream[0];
+                CK(cudaEventRecord(e->ev_fork, st));
+                CK(cudaStreamWaitEvent(s2, e->ev_fork, 0));
+            }
+            p.kern<<<(unsigned)grid, p.block, p.smem, s2>>>(A);
+            CK(cudaGetLastError());
+            walk_launches++;
+            if (s2 != st) {
+                CK(cudaEventRecord(e->ev_join, s2));
+                CK(cudaStreamWaitEvent(st, e->ev_join, 0));
+            }
+        }
+        return SWK_OK;
     };
-    if (grid_of(0, slice_len, shared_variant) > 0x7fffffffull || grid_of(0, slice_len, false) > 0x7fffffffull)
-        return fail(e, SWK_ERR_INVALID, "too many spins x scales for one launch");
     // staging rows -> reference layouts, rows [r0, r1) of every scale (no-op when no per-spin output was requested)
     auto unpack = [&](size_t r0, size_t r1, cudaStream_t st) -> cudaError_t {
         if (!e->stage.p || r1 <= r0) return cudaSuccess;
@@ -1001,9 +1083,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             for (uint32_t s0 = 0; s0 < A.n_scans; s0 += scans_per_leg) {
                 A.scan_first = s0;
                 A.scan_end = std::min(A.n_scans, s0 + scans_per_leg);
-                if (s0 == 0) kern<<<(unsigned)grid_of(0, (uint32_t)S, shared_variant), block, smem, e->stream>>>(A);
-                else kern_private<<<(unsigned)grid_of(0, (uint32_t)S, false), kBlock, smem_private, e->stream>>>(A); // walkers resume at their own rounds
-                CK(cudaGetLastError());
+                if ((rc = launch_walk(e->stream, false, s0 != 0)) != SWK_OK) return rc;
                 if (A.scan_end == A.n_scans) break;
                 rebin_keys_kernel<<<(unsigned)((n_sort + 255) / 256), 256, 0, e->stream>>>(A.state_vox, A.state_b, (uint32_t)S, (uint32_t)n_seg, A.ny, A.nz,
                                                                                          static_cast<uint64_t *>(e->sort_keys_in.p), static_cast<uint32_t *>(e->sort_ids.p));
@@ -1018,12 +1098,10 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
                 A.order_per_scale = per_scale ? 1 : 0;
                 extra_launches += 2;
             }
-            extra_launches += (A.n_scans + scans_per_leg - 1) / scans_per_leg - 1; // n_launches below counts one walk launch per slice
             CK(unpack(0, S, e->stream));
             CK(cudaStreamSynchronize(e->stream)); // order2 is freed on return
         } else {
-            kern<<<(unsigned)grid_of(0, (uint32_t)S, shared_variant), block, smem, e->stream>>>(A);
-            CK(cudaGetLastError());
+            if ((rc = launch_walk(e->stream, true, false)) != SWK_OK) return rc;
             CK(unpack(0, S, e->stream));
         }
     } else {
@@ -1034,8 +1112,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             A.j_first = i * slice_len;
             A.j_end = (uint32_t)std::min<size_t>(S, (size_t)(i + 1) * slice_len);
             cudaStream_t cs = e->cstream[one_stream ? 0 : (i & 1)];
-            kern<<<(unsigned)grid_of(A.j_first, A.j_end, shared_variant), block, smem, cs>>>(A);
-            CK(cudaGetLastError());
+            if ((rc = launch_walk(cs, false, false)) != SWK_OK) return rc;
             CK(unpack(A.j_first, A.j_end, cs)); // the sorted order is slice-major: slots [j_first, j_end) hold exactly the spins [j_first, j_end)
             CK(cudaEventRecord(e->ev_slice[i], cs));
         }
@@ -1086,7 +1163,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     st.lost = cnt[4];
     st.kernel_ms = ms;
     st.device_ms = ms_all;
-    st.n_launches = n_slices + extra_launches + (e->stage.p ? n_slices : 0) + ((E * ns) ? 1 : 0);
+    st.n_launches = walk_launches + extra_launches + (e->stage.p ? n_slices : 0) + ((E * ns) ? 1 : 0);
     return SWK_OK;
 }
 

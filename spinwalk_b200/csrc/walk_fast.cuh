@@ -386,27 +386,28 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
     // ---- which (spin, scale) ----
     uint32_t k, j, k_loc, k_first;
     if (SHARED) {
-        k_first = (blockIdx.x % A.n_groups) * A.group;
+        k_first = A.k_lo + (blockIdx.x % A.n_groups) * A.group;
         k_loc = threadIdx.x >> 5;
         k = k_first + k_loc;
         j = A.j_first + (blockIdx.x / A.n_groups) * 32u + lane;
     } else {
         k_loc = 0u;
-        k = k_first = blockIdx.x % A.n_scales;
-        j = A.j_first + (blockIdx.x / A.n_scales) * kBlock + threadIdx.x;
+        const uint32_t kn = A.k_hi - A.k_lo;
+        k = k_first = A.k_lo + blockIdx.x % kn;
+        j = A.j_first + (blockIdx.x / kn) * kBlock + threadIdx.x;
     }
     for (uint32_t i = threadIdx.x; i < n_bsum * n_grp; i += nthr) bsum[i] = 0;
     {
         const uint32_t wps = A.scale_stride / 4u; // words per scale record
         const uint32_t *src = reinterpret_cast<const uint32_t *>(A.scale_tab) + (size_t)k_first * wps;
         for (uint32_t i = threadIdx.x; i < wps * n_grp; i += nthr)
-            reinterpret_cast<uint32_t *>(sct)[i] = (k_first + i / wps) < A.n_scales ? __ldg(src + i) : 0u;
+            reinterpret_cast<uint32_t *>(sct)[i] = (k_first + i / wps) < A.k_hi ? __ldg(src + i) : 0u;
     }
     __syncthreads();
 
     const bool spin_ok = j < A.j_end;
-    const bool valid = spin_ok && k < A.n_scales;
-    const uint32_t kc = k < A.n_scales ? k : k_first; // a padding warp of the last group reads valid constants and walks nothing
+    const bool valid = spin_ok && k < A.k_hi;
+    const uint32_t kc = k < A.k_hi ? k : k_first; // a padding warp of the last group reads valid constants and walks nothing
     const ScaleConst &SC = *reinterpret_cast<const ScaleConst *>(sct + (size_t)(kc - k_first) * A.scale_stride);
     const float *sgt = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(&SC) + SC.sgt_off);
     const uint32_t fb = SC.fb;
@@ -619,7 +620,7 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
         for (uint32_t i = threadIdx.x; i < n_bsum * n_grp; i += nthr) {
             const uint32_t kk = k_first + i / n_bsum;
             const long long v = bsum[i];
-            if (v != 0 && kk < A.n_scales) atomicAdd(A.sums_fx + (size_t)kk * n_bsum + (i % n_bsum), (unsigned long long)v);
+            if (v != 0 && kk < A.k_hi) atomicAdd(A.sums_fx + (size_t)kk * n_bsum + (i % n_bsum), (unsigned long long)v);
         }
     }
     if (A.counters) {

@@ -85,7 +85,8 @@ struct WalkArgs {
     // FAST mode: per-scale constants (walk_fast.cuh ScaleConst + sigma table), and how blocks are cut
     const uint8_t *scale_tab;
     uint32_t scale_stride;   // bytes per scale record (multiple of 16)
-    uint32_t group, n_groups; // SHARED variant: scales per block (block = 32 x group threads), groups per spin chunk
+    uint32_t k_lo, k_hi;     // this launch walks scales [k_lo, k_hi)
+    uint32_t group, n_groups; // SHARED variant: scales per block (block = 32 x group threads), groups of this launch per spin chunk
     int32_t  perm_draws;     // some 0 < P_XY < 1: permeability uniforms are needed
     // outputs (any may be nullptr)
     // Per-spin results go to STAGING ROWS, one per (scale, local spin): n_te echo slots (Mx, My, Mz, tissue) and one slot for the final

@@ -61,14 +61,25 @@ def _compare(name, fast, ref, n_sub, scales, min_count=200):
     tot_f = (mf * cf[..., None]).sum(axis=2) / np.maximum(cf.sum(axis=2), 1)[..., None]
     tot_r = (mr * cr[..., None]).sum(axis=2) / np.maximum(cr.sum(axis=2), 1)[..., None]
     sig_f, sig_r = np.hypot(tot_f[..., 0], tot_f[..., 1]), np.hypot(tot_r[..., 0], tot_r[..., 1])
-    print(f"\n[{name}] {S} spins x {len(scales)} scales: max (|delta| - floor) / SE = {z.max():.2f} at scale {scales[k]:g} echo {e} substrate {s} "
-          f"component {'xyz'[c]} (delta {d[k, e, s, c]:.3g}, SE {comb[k, e, s, c]:.3g}); max |d|S|| = {np.abs(sig_f - sig_r).max():.3g}; "
-          f"|S| fast {np.array2string(sig_f[:, -1], precision=4, max_line_width=400)} ref {np.array2string(sig_r[:, -1], precision=4, max_line_width=400)}")
+    report = (f"[{name}] {S} spins x {len(scales)} scales: max (|delta| - floor) / SE = {z.max():.2f} at scale {scales[k]:g} echo {e} substrate {s} "
+              f"component {'xyz'[c]} (delta {d[k, e, s, c]:.3g}, SE {comb[k, e, s, c]:.3g}); max |d|S|| = {np.abs(sig_f - sig_r).max():.3g}; "
+              f"|S| fast {np.array2string(sig_f[:, -1], precision=4, max_line_width=400)} ref {np.array2string(sig_r[:, -1], precision=4, max_line_width=400)}")
+    print("\n" + report)
+    try:  # kept with the run's artefacts (gpurun merges gpurun_out/ back)
+        import os
+
+        d_out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(d_out, exist_ok=True)
+        with open(os.path.join(d_out, "parity_report.txt"), "a") as fh:
+            fh.write(report + "\n")
+    except OSError:
+        pass
     assert (excess <= 0).all(), (f"{name}: ensemble mismatch, worst {z.max():.2f} SE at scale {scales[k]:g} echo {e} substrate {s} component {'xyz'[c]}: "
                                  f"fast {mf[k, e, s, c]:.6f} ref {mr[k, e, s, c]:.6f} SE {comb[k, e, s, c]:.2e}")
     # tissue occupancy at the echo (fraction of the written spins found in each substrate)
     pf, pr = cf / np.maximum(cf.sum(axis=2, keepdims=True), 1), cr / np.maximum(cr.sum(axis=2, keepdims=True), 1)
-    tol = NSIG * np.sqrt((pr * (1 - pr) + pf * (1 - pf)) / S) + 1e-6
+    nf, nr = np.maximum(cf.sum(axis=2, keepdims=True), 1), np.maximum(cr.sum(axis=2, keepdims=True), 1)  # spins that wrote the echo
+    tol = NSIG * np.sqrt(pr * (1 - pr) / nr + pf * (1 - pf) / nf) + 1e-6
     assert (np.abs(pf - pr) <= tol).all(), f"{name}: tissue occupancy differs by {np.abs(pf - pr).max():.3g} (tolerance {tol.max():.3g})"
     return z.max()
 
@@ -97,17 +108,26 @@ def _setup(workload, n_spins, scales_pick=None, **override):
 
 
 def test_c1_full_size_vs_reference_cu_sim(engine_lib):
-    """BASELINE configs[0] at full size: GRE, 100^3 cylinder phantom, 1e5 spins x the 50 FoV scales of config_default.ini."""
+    """BASELINE configs[0] at full size: GRE, 100^3 cylinder phantom, 1e5 spins x the 50 FoV scales of config_default.ini.
+    The reference is run on the 44 scales >= 0.0333 (FoV >= 3.3 um = 10.5 sigma): below that its kernel abandons nearly every spin through the
+    out-of-range exit of kernels.cu:141-147 (a step longer than the distance to BOTH walls) and floods the device printf buffer; FAST keeps such a
+    spin in place, so those six scales have no reference to be compared with."""
     sw, po, eng, cfg, case, mask, fm, fov, xyz0 = _setup("c1", 100_000)
     with eng:
         fast = eng.run(xyz0, mode=sw.MODE_FAST)
-    ref = po.run_ref_cuda(case, fm, mask, xyz0)
     scales = np.asarray(cfg.scales)
+    first = int(np.argmax(scales >= 0.0333))
+    case.scales = [float(s) for s in scales[first:]]
+    ref = po.run_ref_cuda(case, fm, mask, xyz0)
     lost_ref = (~(ref["M1"] != 0).any(axis=3)).sum(axis=(1, 2))
-    print(f"\n[c1] reference lost spins per scale (double wrap, FoV < 4 um): {dict((float(s), int(n)) for s, n in zip(scales, lost_ref) if n)}")
-    assert fast["stats"]["lost"] == 0
-    assert (lost_ref[scales >= 0.046] == 0).all(), "the reference loses spins only where the FoV is a few step lengths wide"
-    _compare("c1", fast, ref, 2, scales)
+    print(f"\n[c1] reference lost spins per scale (double wrap): {dict((float(s), int(n)) for s, n in zip(scales[first:], lost_ref) if n)}")
+    assert fast["stats"]["lost"] == 0 and fast["M1"].shape[0] == 50
+    assert (lost_ref[scales[first:] >= 0.046] == 0).all(), "the reference loses spins only where the FoV is a few step lengths wide"
+    assert lost_ref.sum() <= 200
+    part = {k: v[first:] for k, v in fast.items() if k in ("M1", "T", "XYZ1")}
+    _compare("c1", part, ref, 2, scales[first:])
+    # the six smallest scales: every spin is still there and carries a unit-length magnetisation history (|M| <= 1)
+    assert np.isfinite(fast["M1"][:first]).all() and (np.abs(fast["M1"][:first]) <= 1.0 + 1e-5).all() and (fast["M1"][:first] != 0).any(axis=3).all()
 
 
 def test_c2_sample_vs_reference_cu_sim(engine_lib):
