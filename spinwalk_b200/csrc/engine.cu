@@ -936,7 +936,14 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         auto shared_bytes = [&](uint32_t g) { return ((bsum_bytes * g + 15) & ~size_t(15)) + (size_t)stride * g + (size_t)ES_FIELDS * 4 * 32 * g + nbuf_bytes; };
         double sig_thr = 1.25;
         if (const char *ev = getenv("SWK_SHARE_SIGMA")) sig_thr = atof(ev); // tuning knob
-        const bool share_off = (flags & SWK_RUN_NO_SHARE) || getenv("SWK_NO_SHARE") != nullptr;
+        bool share_off = (flags & SWK_RUN_NO_SHARE) || getenv("SWK_NO_SHARE") != nullptr;
+        // A voxel table that lives in HBM (no z slab, larger than L2): the launch as a whole runs at the random-access rate of the memory, and what
+        // matters is that gather-bound and issue-bound blocks share every SM — one PRIVATE launch over all scales does that (measured on C2's full
+        // table: 557 ms against 632 ms for the two-launch cut, profiles/README.md).
+        {
+            const size_t table_bytes = A.packed ? (use_slab ? e->slab.bytes : e->packed.bytes) : (size_t)A.V * (A.fieldmap ? 5 : 1);
+            if (table_bytes > (size_t)100e6 && getenv("SWK_SHARE_SIGMA") == nullptr) share_off = true;
+        }
         std::vector<char> want_shared(n_scales, 0);
         {
             const double *sig = reinterpret_cast<const double *>(e->blob_h.data() + e->L.sigma);

@@ -76,7 +76,8 @@ def test_cli_compat_equals_reference_kernel(cli, oracle, tmp_path):
     assert r.returncode == 0, r.stderr
     assert "Simulation completed successfully" in r.stdout
     out = str(tmp_path / "out" / "se_test_phantom.h5")
-    assert sorted(h5util.names(out)) == ["M", "T", "TE", "XYZ", "scales", "sums"]
+    assert sorted(h5util.names(out)) == ["M", "T", "TE", "XYZ", "scales", "sums", "swk_mode", "swk_seed"]
+    assert h5util.read(out, "swk_mode").ravel().tolist() == [0] and h5util.read(out, "swk_seed").ravel().tolist() == [case.seed]  # which arithmetic wrote the file
     # the INI route rounds DIFFUSIVITY through float (std::stof, config_reader.cpp:164), as the reference does
     case.diffusivity = [float(np.float32(1.0e-9))] * 2
     ref = oracle.run_ref_cuda(case, fm, mask, xyz0)  # xyz0 = the oracle's restatement of the mt19937 start positions
@@ -107,10 +108,63 @@ def test_cli_two_engines_equal_one(cli, tmp_path):
     assert (outs[0]["M"] != 0).any()
 
 
+def test_cli_sums_only_and_device_positions(cli, tmp_path):
+    """--sums-only: no per-spin arrays anywhere (what lets BASELINE's 1e9-spin configuration run through the command line); the sums equal
+    those of the full run (fixed-point accumulation: exactly), on one or several engines, more engines than spins included.
+    --device-positions: start positions drawn on the GPU; every spin is counted at the echo."""
+    S = 5000
+    _stage(tmp_path, S)
+    ini, out = str(tmp_path / "se.ini"), str(tmp_path / "out" / "se_test_phantom.h5")
+    r = subprocess.run([cli, "sim", "-c", ini, "--sums", "-q"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    full = h5util.read(out, "sums")
+    M, T = h5util.read(out, "M"), h5util.read(out, "T")
+    for sub in range(2):  # the sums are the per-spin outputs added up per substrate
+        w = T[..., 0] == sub
+        assert np.array_equal(full[:, :, sub, 3], w.sum(axis=1).astype(np.float64))
+        assert np.allclose(full[:, :, sub, :3], (M.astype(np.float64) * w[..., None]).sum(axis=1), rtol=0, atol=S * 2.0 ** -22)
+    for dev in ("0", "0,0,0"):
+        r = subprocess.run([cli, "sim", "-c", ini, "--sums-only", "-d", dev, "-q"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert sorted(h5util.names(out)) == ["TE", "scales", "sums", "swk_mode", "swk_seed"]
+        assert np.array_equal(h5util.read(out, "sums"), full), dev
+        assert h5util.read(out, "swk_mode").ravel().tolist() == [1]
+    r = subprocess.run([cli, "sim", "-c", ini, "--sums-only", "--device-positions", "-q"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    dp = h5util.read(out, "sums")
+    assert (dp[..., 3].sum(axis=2) == S).all() and not np.array_equal(dp, full)
+    tot_a, tot_b = full.sum(axis=2)[:, 0], dp.sum(axis=2)[:, 0]
+    assert np.abs(np.hypot(tot_a[:, 0], tot_a[:, 1]) - np.hypot(tot_b[:, 0], tot_b[:, 1])).max() / S < 0.03  # same ensemble, other start positions
+    # more devices than spins: no empty shard
+    (tmp_path / "two.ini").write_text(INI.format(S=2))
+    r = subprocess.run([cli, "sim", "-c", str(tmp_path / "two.ini"), "--sums-only", "-d", "0,0,0", "-q"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (h5util.read(str(tmp_path / "out" / "se_test_phantom.h5"), "sums")[..., 3].sum(axis=2) == 2).all()
+
+
+def test_output_file_opens_with_libhdf5(cli, tmp_path):
+    """the h5lite-written output through a real libhdf5 (h5py), when this image has one — the side of the codec tests/h5spec.py stands in for"""
+    h5py = pytest.importorskip("h5py")
+    S = 300
+    _stage(tmp_path, S)
+    r = subprocess.run([cli, "sim", "-c", str(tmp_path / "se.ini"), "--sums", "-q"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = str(tmp_path / "out" / "se_test_phantom.h5")
+    with h5py.File(out, "r") as f:
+        assert f["M"].shape == (3, S, 1, 3) and f["XYZ"].shape == (3, S, 1, 3) and f["T"].shape == (3, S, 1, 1) and f["T"].dtype == np.uint8
+        for k in ("M", "XYZ", "T", "scales", "TE", "sums"):
+            assert np.array_equal(f[k][...], h5util.read(out, k)), k
+
+
 def test_cli_error_conventions(cli, tmp_path):
     _stage(tmp_path, 64)
     r = subprocess.run([cli, "sim", "-c", str(tmp_path / "se.ini"), "-p"], capture_output=True, text=True)
-    assert r.returncode == 1 and "no CPU path" in r.stderr
+    assert r.returncode == 0 and "no CPU path" in r.stderr and "warning" in r.stderr  # -p: accepted, warned about, run on the GPU (SURVEY §8b)
+    for bad in ("0,", "a", "0,,1", "-1"):
+        r = subprocess.run([cli, "sim", "-c", str(tmp_path / "se.ini"), "-d", bad], capture_output=True, text=True)
+        assert r.returncode == 1 and "not a device id" in r.stderr, bad
+    r = subprocess.run([cli, "sim", "-c", str(tmp_path / "se.ini"), "-d", "999"], capture_output=True, text=True)
+    assert r.returncode == 1 and "not available" in r.stderr
     r = subprocess.run([cli, "sim", "-c", str(tmp_path / "missing.ini")], capture_output=True, text=True)
     assert r.returncode == 1 and "does not exist" in r.stderr
     (tmp_path / "one.ini").write_text(INI.format(S=64).replace("DIFFUSIVITY[1] = 1.0e-9\n", "").replace("T1[1] = 2200\n", "").replace("T2[1] = 41\n", "")
