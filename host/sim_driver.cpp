@@ -216,8 +216,10 @@ bool run_one(const std::string &config_file, const SimOptions &opt, std::string 
         w.add("TE", {E, 1, 1, 1}, te_s);
         if (opt.write_sums) w.add("sums", {K, E, ns, 4}, sums);
         // which arithmetic produced the file (the reference has one; this engine has two): 0 = --compat (the reference's, spin by spin), 1 = fast
-        w.add("swk_mode", {1}, std::vector<uint8_t>{(uint8_t)(opt.compat ? SWK_MODE_COMPAT : SWK_MODE_FAST)});
-        w.add("swk_seed", {1}, std::vector<uint64_t>{(uint64_t)P.seed});
+        const std::vector<uint8_t> mode_v{(uint8_t)(opt.compat ? SWK_MODE_COMPAT : SWK_MODE_FAST)}; // (the writer keeps pointers until close())
+        const std::vector<uint64_t> seed_v{(uint64_t)P.seed};
+        w.add("swk_mode", {1}, mode_v);
+        w.add("swk_seed", {1}, seed_v);
         if (!w.close()) { err = w.error(); return false; }
         if (!opt.quiet) fprintf(stderr, "Saved %s\n", out.c_str());
     }

@@ -494,8 +494,7 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
 
     // ======================================= one attempt =======================================
     // one tentative step (kernels.cu:130-170) with the normals of round `r`; `perm_u` yields the permeability uniform of the round;
-    // `overlap` is independent work placed between ISSUING the voxel gather and CONSUMING it (PRIVATE variant: the random numbers of the
-    // next rounds, so that a thread covers part of its own gather latency — what matters when the table lives in HBM).
+    // `overlap` is a hook for independent work between ISSUING the voxel gather and CONSUMING it (unused today, see the PRIVATE loop below).
     auto attempt = [&](const float a0, const float a1, const float a2, const uint32_t r, auto &&perm_u, auto &&overlap) {
         const bool act = rem > 0;
         uint32_t q0 = fx_step(p0, a0, sg0), q1 = fx_step(p1, a1, sg1), q2 = fx_step(p2, a2, sg2);
@@ -602,18 +601,17 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
             cur ^= 1u;
         }
     } else {
-        // The integer half of the next Philox block (the ten rounds) overlaps the gather of the even round, its float half (Box-Muller) that
-        // of the odd round.
+        // (Overlapping the next block's Philox rounds / Box-Muller with the gathers of these two attempts, as the round-1 kernel did, was measured
+        // again on this kernel: the ten extra live registers spill inside the loop and the walk gets 19 % slower; profiles/README.md.)
         uint32_t r = r_first;
-        float na0, na1, na2, nb0, nb1, nb2;
-        normals6_fast(philox_fixed(r >> 1, seed_lo, spin_no, seed_hi_walk), kOne, na0, na1, na2, nb0, nb1, nb2);
         auto pu = [&](uint32_t rr) { return u01_open1(philox2x32_10(rr, spin_no, A.perm_key)); };
         while (!done) {
 #pragma unroll 1
             for (uint32_t h = 0; h < kSync; h += 2u) {
-                uint4 raw;
-                attempt(na0, na1, na2, r, pu, [&] { raw = philox_fixed((r >> 1) + 1u, seed_lo, spin_no, seed_hi_walk); });
-                attempt(nb0, nb1, nb2, r + 1u, pu, [&] { normals6_fast(raw, kOne, na0, na1, na2, nb0, nb1, nb2); });
+                float a0, a1, a2, b0, b1, b2;
+                normals6_fast(philox_fixed(r >> 1, seed_lo, spin_no, seed_hi_walk), kOne, a0, a1, a2, b0, b1, b2);
+                attempt(a0, a1, a2, r, pu, [] {});
+                attempt(b0, b1, b2, r + 1u, pu, [] {});
                 r += 2u;
             }
             if (rem == 0) advance(r);
