@@ -926,6 +926,30 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             const uint32_t *run = reinterpret_cast<const uint32_t *>(e->blob_h.data() + e->L.tl_run);
             for (uint32_t i = 0; i < e->L.n_tl; i++) gruns |= run[i] >= 2u;
         }
+        { // nominal rounds of one TR for a walker that is never rejected: its segments (walk_fast.cuh advance_walker), each ending at a sync round
+            const int32_t *tl_time = reinterpret_cast<const int32_t *>(e->blob_h.data() + e->L.tl_time);
+            const uint32_t *tl_run = reinterpret_cast<const uint32_t *>(e->blob_h.data() + e->L.tl_run);
+            const uint32_t n_tp = A.n_tp;
+            uint32_t r = 0, t = 0;
+            auto seg = [&](uint32_t stop) {
+                if (stop > t) { r = (r + (stop - t) + kSync - 1) / kSync * kSync; t = stop; }
+            };
+            for (uint32_t ev = 0; ev < e->L.n_tl;) {
+                const uint32_t ev_time = (uint32_t)tl_time[ev];
+                if (ev_time >= n_tp) break;
+                if (gruns && tl_run[ev] >= 2u) {
+                    const uint32_t len = std::min(tl_run[ev], n_tp - ev_time);
+                    seg(ev_time);
+                    seg(ev_time + len);
+                    ev += len;
+                } else {
+                    seg(ev_time + 1u);
+                    ev++;
+                }
+            }
+            seg(n_tp);
+            A.tr_period = (r + 2u + n_tp / 64u + kSync - 1) / kSync * kSync;
+        }
         const size_t fixed_private = ((bsum_bytes + 15) & ~size_t(15)) + stride + (size_t)ES_FIELDS * 4 * kBlock;
         if (fixed_private > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
         // SHARED variant (walk_fast.cuh): 32 spins x G scales per block share the spins' normals: ~45 instead of ~90 instructions per attempt

@@ -30,6 +30,9 @@
 #ifndef SWK_FAST_SHARED_MAXT
 #define SWK_FAST_SHARED_MAXT 320 // SHARED variant: at most 10 scales (warps) per block
 #endif
+#ifndef SWK_FAST_UNROLL
+#define SWK_FAST_UNROLL 4   // rounds unrolled in the SHARED loop (8 with prefetch spills ~10 values per attempt at 48 registers; 4: none)
+#endif
 #ifndef SWK_FAST_SHARED_MINB
 #define SWK_FAST_SHARED_MINB 4   // ... and at most 65536 / (4 x 320) = 51 -> 48 registers: 40 warps per SM
 #endif
@@ -151,6 +154,7 @@ __device__ __forceinline__ uint32_t ldg_voxel(const uint32_t *p)
 // fetched from its [nx][ny] slab: the same words as variant 2 from a table nz times smaller (L1/L2 resident).
 enum { VOX_MASK = 0, VOX_SPLIT = 1, VOX_PACKED = 2, VOX_SLAB = 3 };
 
+constexpr int kUnroll = SWK_FAST_UNROLL;
 constexpr uint32_t kSync = 8;   // a walker runs its sequence events at rounds that are multiples of kSync (see the file header)
 constexpr uint32_t kBatch = 16; // SHARED variant: rounds of normals generated per barrier (32 spins x 16 rounds = 256 Philox blocks)
 
@@ -298,6 +302,13 @@ __device__ __noinline__ AdvOut advance_walker(const AdvCtx *cx, const uint32_t p
             ev += run_len;
         } else {
             if (seg == SEG_TAIL) { // end of TR (kernels.cu:226-231)
+                // RE-SYNCHRONISATION of multi-TR runs.  Every permeability rejection costs a walker one round, so the lanes of a warp reach their
+                // events at different rounds and — over the ~1100 TRs of a bSSFP run — drift apart completely: the event code below would run once
+                // per lane instead of once per warp.  TR number i therefore ends no earlier than round (i + 1) x A.tr_period, where the period
+                // (engine.cu) is what a walker without rejections needs for a TR plus a slack of 2 + timepoints / 64 rounds: walkers that lose
+                // fewer rounds than the slack per TR — nearly all, except behind walls at small FoV scales — stay on the common schedule, and a
+                // walker that fell behind catches up by the slack of every TR.  Deterministic per walker (absolute round numbers).
+                if (scan + 1 < A.n_scans && r_next < (scan + 1u) * A.tr_period) break; // called again at the next sync round (rem stays 0); also before a re-binning pause
                 const float dt_s = (float)((double)((n_tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
                 dephase_relax(m, acc, tT1[ts], tT2[ts], dt_s);
                 scan++;
@@ -305,6 +316,9 @@ __device__ __noinline__ AdvOut advance_walker(const AdvCtx *cx, const uint32_t p
             }
             { // start of a TR: phase cycling + first RF (kernels.cu:110-126)
                 float ph = (float)((double)(A.rf_ph0 + (float)scan * SC.lin_pc) + (double)(scan * (scan + 1u)) / 2.0 * (double)A.quad_pc);
+                // the reference wraps by repeated subtraction (kernels.cu:112-113: hundreds of iterations late in a bSSFP run): whole turns in closed form first
+                if (ph > 720.f) ph = (float)((double)ph - 360.0 * floor(((double)ph - 360.0) / 360.0));
+                if (ph < -360.f) ph = (float)((double)ph + 360.0 * floor(-(double)ph / 360.0));
                 while (ph > 360.0) ph = (float)(ph - 360.0);
                 while (ph < 0) ph = (float)(ph + 360.0);
                 float rr[3];
@@ -586,11 +600,9 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
 #pragma unroll 1
                 for (uint32_t h = 0; h < kBatch; h += kSync) {
                     const float4 *nb = nbuf + cur * (kBatch * 32u) + h * 32u + lane;
-                    float4 n = nb[0];
-#pragma unroll
+#pragma unroll kUnroll
                     for (uint32_t rr = 0; rr < kSync; rr++) {
-                        const float4 c = n;
-                        if (rr + 1u < kSync) n = nb[(rr + 1u) * 32u]; // the next round's normals are in flight while this one is taken
+                        const float4 c = nb[rr * 32u];
                         attempt(c.x, c.y, c.z, r0 + h + rr, [&](uint32_t) { return c.w; }, [] {});
                     }
                     if (rem == 0) advance(r0 + h + kSync);

@@ -88,6 +88,7 @@ struct WalkArgs {
     uint32_t k_lo, k_hi;     // this launch walks scales [k_lo, k_hi)
     uint32_t group, n_groups; // SHARED variant: scales per block (block = 32 x group threads), groups of this launch per spin chunk
     int32_t  perm_draws;     // some 0 < P_XY < 1: permeability uniforms are needed
+    uint32_t tr_period;      // FAST mode, multi-TR runs: nominal rounds per TR (walk_fast.cuh: re-synchronisation at TR boundaries)
     // outputs (any may be nullptr)
     // Per-spin results go to STAGING ROWS, one per (scale, local spin): n_te echo slots (Mx, My, Mz, tissue) and one slot for the final
     // position, 16 bytes each — a thread's scattered result write is whole aligned 16/32-byte pieces instead of three partial-sector
