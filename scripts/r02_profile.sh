@@ -9,8 +9,8 @@ SWK_NO_ZSLAB=1 ncu --metrics $M --clock-control none -k regex:"walk_fast|unpack_
 ncu --metrics $M --clock-control none -k regex:"walk_fast" --csv --log-file $O/r02_traffic_c5.csv python bench.py --workload c5 --spins 25000000 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-extras > $O/r02_traffic_c5.log 2>&1
 SWK_NO_ZSLAB=1 ncu --metrics $M --clock-control none -k regex:"walk_fast" --csv --log-file $O/r02_traffic_c5_full.csv python bench.py --workload c5 --spins 25000000 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-extras > $O/r02_traffic_c5_full.log 2>&1
 # full set + source: the two variants of the default path on 2e6 spins (all 50 scales), and three single scales of the SHARED variant
-ncu --set full --import-source on --clock-control none -k regex:"walk_fast_kernel<0" -o $O/r02_full_c2 -f python bench.py --spins 2000000 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-extras > $O/r02_full_c2.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"walk_fast_kernel<0" -o $O/r02_full_scales -f python scripts/scale_sweep.py --modes fast --spins 2000000 --reps 1 --flags 7 --dup 10 --scales 0.0125,1.0301,37.5 > $O/r02_full_scales.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:walk_fast -o $O/r02_full_c2 -f python bench.py --spins 2000000 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-extras > $O/r02_full_c2.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:walk_fast -o $O/r02_full_scales -f python scripts/scale_sweep.py --modes fast --spins 2000000 --reps 1 --flags 7 --dup 10 --scales 0.0125,1.0301,37.5 > $O/r02_full_scales.log 2>&1
 python scripts/make_traffic.py c2:fast=$O/r02_traffic_c2.csv:10000000 c2:fast:full=$O/r02_traffic_c2_full.csv:10000000 c5:fast=$O/r02_traffic_c5.csv:25000000 c5:fast:full=$O/r02_traffic_c5_full.csv:25000000 > $O/r02_traffic_json.log 2>&1
 cp profiles/traffic.json $O/traffic.json
 tail -3 $O/r02_traffic_json.log

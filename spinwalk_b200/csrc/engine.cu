@@ -77,7 +77,7 @@ struct swk_engine {
     bool has_sequence = false;
 
     // spins
-    DevBuf xyz0, m0, order;
+    DevBuf xyz0, m0, order, inv_order; // inv_order: spin -> thread slot (unpack_rows_kernel)
     DevBuf state_a, state_b, state_vox;                     // re-binning pauses of long runs: per (scale, spin) walker state
     DevBuf sort_keys_in, sort_keys_out, sort_ids, sort_tmp; // kept between runs: re-sorting after every swk_set_spins must not malloc
     bool order_valid = false;
@@ -255,17 +255,20 @@ __global__ void rebin_keys_kernel(const uint32_t *state_vox, const uint4 *state_
     ids[i] = (uint32_t)(i % n_local);
 }
 
-// Staging rows -> the reference's output layouts (monte_carlo.cu:61-70), rows [r0, r1) of every scale: a streaming pass, one 16-byte
-// slot per thread, consecutive threads write consecutive elements of M1 / T / XYZ1.
-__global__ void unpack_rows_kernel(const uint4 *stage, uint32_t row_slots, uint32_t n_te, size_t S, size_t r0, size_t r1, uint32_t K, float *M1, uint8_t *T,
-                                   float *XYZ1)
+// Staging rows -> the reference's output layouts (monte_carlo.cu:61-70), rows [r0, r1) of every scale: a streaming pass over the OUTPUT, one
+// 16-byte slot per thread; consecutive threads write consecutive elements of M1 / T / XYZ1.  The walkers wrote their rows in thread-slot order
+// (whole 512-byte lines per warp); `inv` (inverse of the locality order: spin -> thread slot) un-permutes them here, with 16-byte gathers.
+__global__ void unpack_rows_kernel(const uint4 *stage, uint32_t row_slots, uint32_t n_te, size_t S, size_t chunks, size_t r0, size_t r1, uint32_t K,
+                                   const uint32_t *inv, float *M1, uint8_t *T, float *XYZ1)
 {
     const size_t per_scale = (r1 - r0) * row_slots, total = per_scale * K;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t k = i / per_scale, rem = i - k * per_scale;
-        const size_t row = k * S + r0 + rem / row_slots;
+        const size_t r = r0 + rem / row_slots, row = k * S + r;
         const uint32_t e = (uint32_t)(rem % row_slots);
-        const uint4 v = __ldcs(stage + row * row_slots + e);
+        const size_t slot = inv ? (size_t)__ldg(inv + r) : r;
+        uint4 v; // one 16-byte gather per output slot; L2::64B: do not pull the whole 128-byte line of somebody else's rows from HBM
+        asm("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(stage + ((k * chunks + (slot >> 5)) * row_slots + e) * 32u + (slot & 31u)));
         if (e < n_te) {
             if (M1) {
                 float *d = M1 + (row * n_te + e) * 3;
@@ -277,6 +280,13 @@ __global__ void unpack_rows_kernel(const uint4 *stage, uint32_t row_slots, uint3
             __stcs(d + 0, __uint_as_float(v.x)); __stcs(d + 1, __uint_as_float(v.y)); __stcs(d + 2, __uint_as_float(v.z));
         }
     }
+}
+
+// inverse of the locality order: inv[order[j]] = j
+__global__ void invert_order_kernel(const uint32_t *order, uint32_t n, uint32_t *inv)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) inv[order[j]] = j;
 }
 
 // fixed-point ensemble sums (walk_kernel.cuh echo_sums_add) -> double [K][E][n_sub][4]
@@ -410,7 +420,7 @@ void swk_destroy(swk_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     for (DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab})
+                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
         release(*b);
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -734,7 +744,8 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     if ((rc = ensure(e, e->M1, (flags & SWK_OUT_M1) ? K * S * E * 3 * sizeof(float) : 0)) != SWK_OK) return rc;
     if ((rc = ensure(e, e->XYZ1, (flags & SWK_OUT_XYZ1) ? K * S * e->trj * 3 * sizeof(float) : 0)) != SWK_OK) return rc;
     if ((rc = ensure(e, e->T, (flags & SWK_OUT_T) ? K * S * E : 0)) != SWK_OK) return rc;
-    if ((rc = ensure(e, e->stage, want_stage ? K * S * stage_row * sizeof(uint4) : 0)) != SWK_OK) return rc;
+    const size_t stage_chunks = (S + 31) / 32;
+    if ((rc = ensure(e, e->stage, want_stage ? K * stage_chunks * stage_row * 32 * sizeof(uint4) : 0)) != SWK_OK) return rc;
     if ((rc = ensure(e, e->sums, std::max<size_t>(K * E * ns * 4, 1) * sizeof(double))) != SWK_OK) return rc;
     if ((rc = ensure(e, e->sums_fx, std::max<size_t>(K * E * ns * 4, 1) * sizeof(unsigned long long))) != SWK_OK) return rc;
     if ((rc = ensure(e, e->counters, 8 * sizeof(unsigned long long))) != SWK_OK) return rc;
@@ -794,9 +805,12 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             if (ce != cudaSuccess) rs = fail(e, SWK_ERR_CUDA, std::string("spin ordering: ") + cudaGetErrorString(ce));
         }
         if (rs != SWK_OK) return rs;
+        if ((rs = ensure(e, e->inv_order, S * sizeof(uint32_t))) != SWK_OK) return rs;
+        invert_order_kernel<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(static_cast<const uint32_t *>(e->order.p), (uint32_t)S, static_cast<uint32_t *>(e->inv_order.p));
+        CK(cudaGetLastError());
         e->order_valid = true;
         e->order_slice = want_order_slice;
-        extra_launches++;
+        extra_launches += 2;
     }
 
     tr.mark("spin ordering");
@@ -874,6 +888,8 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     A.n_local = e->n_local;
     A.stage = static_cast<uint4 *>(e->stage.p);
     A.stage_row = (uint32_t)stage_row;
+    A.stage_chunks = (uint32_t)stage_chunks;
+    A.stage_by_slot = 1; // (re-binned runs, whose order changes between legs, index their rows by the spin: set below)
     A.XYZ1 = record ? static_cast<float *>(e->XYZ1.p) : nullptr;
     A.sums_fx = (E * ns) ? static_cast<unsigned long long *>(e->sums_fx.p) : nullptr;
     A.counters = static_cast<unsigned long long *>(e->counters.p);
@@ -1065,7 +1081,8 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         if (!e->stage.p || r1 <= r0) return cudaSuccess;
         const size_t total = (r1 - r0) * stage_row * K;
         const unsigned g = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)e->sm_count * 32);
-        unpack_rows_kernel<<<g, 256, 0, st>>>(static_cast<const uint4 *>(e->stage.p), (uint32_t)stage_row, (uint32_t)E, S, r0, r1, (uint32_t)K,
+        unpack_rows_kernel<<<g, 256, 0, st>>>(static_cast<const uint4 *>(e->stage.p), (uint32_t)stage_row, (uint32_t)E, S, stage_chunks, r0, r1, (uint32_t)K,
+                                             (A.stage_by_slot && e->order_valid) ? static_cast<const uint32_t *>(e->inv_order.p) : nullptr,
                                              static_cast<float *>(e->M1.p), static_cast<uint8_t *>(e->T.p), record ? nullptr : static_cast<float *>(e->XYZ1.p));
         return cudaGetLastError();
     };
@@ -1105,6 +1122,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
                 (rc = ensure(e, e->state_vox, n_state * sizeof(uint32_t))) != SWK_OK || (rc = ensure(e, e->sort_keys_in, n_sort * 8)) != SWK_OK ||
                 (rc = ensure(e, e->sort_keys_out, n_sort * 8)) != SWK_OK || (rc = ensure(e, e->sort_ids, n_sort * 4)) != SWK_OK)
                 return rc;
+            A.stage_by_slot = 0;
             A.state_a = static_cast<uint4 *>(e->state_a.p);
             A.state_b = static_cast<uint4 *>(e->state_b.p);
             A.state_vox = static_cast<uint32_t *>(e->state_vox.p);
@@ -1342,7 +1360,7 @@ uint64_t swk_device_bytes(const swk_engine *e)
     if (!e) return 0;
     uint64_t n = 0;
     for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab})
+                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
         n += b->bytes;
     return n;
 }

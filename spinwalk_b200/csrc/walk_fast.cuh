@@ -202,17 +202,60 @@ __device__ __noinline__ void generate_normals(float4 *buf, const uint32_t r0, co
 enum : uint32_t { ES_M0 = 0u, ES_M1, ES_M2, ES_SCAN, ES_EV, ES_SEG, ES_TSTOP, ES_TOLD, ES_RF, ES_TE, ES_DEPH, ES_GFIRST, ES_RUNLEN, ES_FIELDS };
 
 // ======================================= events (out of line) =======================================
-// Cold per-walker context of advance_walker, built once per thread (lives in local memory: it is only read at events).
-struct AdvCtx {
-    const WalkArgs *A;     // the kernel's parameter block
-    const uint8_t *B;      // sequence tables (shared memory when they fit, else global)
-    const ScaleConst *SC;  // this walker's scale
-    uint32_t *es;          // this thread's event state, field f at es[f * nthr]
-    long long *bsum;       // block sums of this walker's scale
-    uint4 *stage;          // this walker's staging row, or nullptr
-    size_t st_idx;         // index into the pause-state arrays
-    uint32_t spin_no, nthr, n_bsum;
+// Where a thread's walker lives: scale, thread slot, spin, shared-memory regions.  A pure function of the launch parameters and the
+// thread / block indices, so the out-of-line event code recomputes it instead of receiving a context through local memory.
+template <bool SHARED>
+struct Geo {
+    uint32_t k, k_first, k_loc, j, jl, spin_no, nthr, n_bsum;
+    bool spin_ok, valid;
+    const uint8_t *B;       // sequence tables (shared memory when they fit, else global)
+    long long *bsum;        // block sums, [scales of the block][n_bsum]
+    uint8_t *sct;           // scale constants of the block's scales
+    uint32_t *es;           // this thread's event state, field f at es[f * nthr]
+    float4 *nbuf;           // normals (SHARED)
+    __device__ __forceinline__ Geo(const WalkArgs &A, uint8_t *smem)
+    {
+        nthr = blockDim.x;
+        uint32_t off = A.blob_in_smem ? A.L.bytes : 0u; // (multiple of 16)
+        B = A.blob_in_smem ? smem : A.blob;
+        const uint32_t n_grp = SHARED ? A.group : 1u;
+        n_bsum = A.sums_fx ? A.n_te * A.L.n_sub * 4u : 0u;
+        bsum = reinterpret_cast<long long *>(smem + off);
+        off += (n_bsum * n_grp * 8u + 15u) & ~15u;
+        sct = smem + off;
+        off += A.scale_stride * n_grp;
+        es = reinterpret_cast<uint32_t *>(smem + off) + threadIdx.x;
+        off += ES_FIELDS * 4u * nthr; // (nthr is a multiple of 32: stays 16-byte aligned)
+        nbuf = reinterpret_cast<float4 *>(smem + off);
+        if (SHARED) {
+            k_first = A.k_lo + (blockIdx.x % A.n_groups) * A.group;
+            k_loc = threadIdx.x >> 5;
+            k = k_first + k_loc;
+            j = A.j_first + (blockIdx.x / A.n_groups) * 32u + (threadIdx.x & 31u);
+        } else {
+            const uint32_t kn = A.k_hi - A.k_lo;
+            k_loc = 0u;
+            k = k_first = A.k_lo + blockIdx.x % kn;
+            j = A.j_first + (blockIdx.x / kn) * kBlock + threadIdx.x;
+        }
+        spin_ok = j < A.j_end;
+        valid = spin_ok && k < A.k_hi;
+        if (k >= A.k_hi) k = k_first; // a padding warp of the last group reads valid constants and walks nothing
+        jl = spin_ok ? (A.order ? __ldg(A.order + ((!SHARED && A.order_per_scale) ? (size_t)k * A.n_local : 0) + j) : j) : 0u;
+        spin_no = A.spin_first + jl; // GLOBAL spin id: RNG key and dephasing term
+    }
+    __device__ __forceinline__ const ScaleConst &sc(const WalkArgs &A) const { return *reinterpret_cast<const ScaleConst *>(sct + (size_t)(k - k_first) * A.scale_stride); }
+    __device__ __forceinline__ size_t st_idx(const WalkArgs &A) const { return (size_t)k * A.n_local + jl; }
+    // staging slot e of this walker: rows are laid out per warp-sized chunk of thread slots, structure of arrays — [scale][chunk][slot e][lane] — so a
+    // warp's echo write is 512 contiguous bytes.  Indexed by the thread slot (coalesced; unpack_rows_kernel un-permutes through the inverse order)
+    // or, for the legs of a re-binned run whose order changes, by the spin.
+    __device__ __forceinline__ uint4 *stage(const WalkArgs &A, uint32_t e) const
+    {
+        const uint32_t row = A.stage_by_slot ? j : jl;
+        return A.stage + (((size_t)k * A.stage_chunks + (row >> 5)) * A.stage_row + e) * 32u + (row & 31u);
+    }
 };
+
 struct AdvOut {
     float acc;
     int rem;
@@ -223,17 +266,19 @@ enum : uint32_t { WF_LOST = 1u, WF_DONE = 2u, WF_GRUN = 4u, WF_FRESH = 8u };
 // Called at a round that is a multiple of kSync by a walker whose segment is complete (rem == 0): runs the sequence events that are due
 // (kernels.cu:175-215, 226-231, 110-126) and sets up the next segment; `r_next` is the first round the walker will use afterwards.
 // Out of line on purpose: the event arithmetic (sincos / exp / FP64) must not compete with the registers of the round loop.
-template <bool STATS, bool RECORD, int VOX, bool GRUNS>
-__device__ __noinline__ AdvOut advance_walker(const AdvCtx *cx, const uint32_t p0, const uint32_t p1, const uint32_t p2, const uint32_t wcur, float acc,
+template <bool STATS, bool RECORD, int VOX, bool GRUNS, bool SHARED>
+__device__ __noinline__ AdvOut advance_walker(const WalkArgs *pA, const uint32_t p0, const uint32_t p1, const uint32_t p2, const uint32_t wcur, float acc,
                                               uint32_t cnt_grad, uint32_t flags, const uint32_t r_next)
 {
-    const WalkArgs &A = *cx->A;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const WalkArgs &A = *pA;
     const BlobLayout &L = A.L;
-    const uint8_t *B = cx->B;
-    const ScaleConst &SC = *cx->SC;
-    uint32_t *es = cx->es;
-    const uint32_t nthr = cx->nthr;
-    uint4 *stage = cx->stage;
+    const Geo<SHARED> g(A, smem);
+    const uint8_t *B = g.B;
+    const ScaleConst &SC = g.sc(A);
+    uint32_t *es = g.es;
+    const uint32_t nthr = g.nthr;
+    const bool stage = A.stage != nullptr;
     const uint32_t n_tp = A.n_tp;
     const int32_t  *tl_time = blob_ptr<int32_t>(B, L.tl_time);
     const uint32_t *tl_mask = blob_ptr<uint32_t>(B, L.tl_mask), *tl_run = blob_ptr<uint32_t>(B, L.tl_run);
@@ -258,7 +303,7 @@ __device__ __noinline__ AdvOut advance_walker(const AdvCtx *cx, const uint32_t p
             const uint32_t mask_ev = tl_mask[ev];
             const uint32_t tp = (uint32_t)tl_time[ev];
             if (mask_ev & EV_DEPH) { // kernels.cu:175-178
-                acc += (float)cx->spin_no * blob_ptr<float>(B, L.deph_deg)[cnt_deph] / (float)A.n_spins_global;
+                acc += (float)g.spin_no * blob_ptr<float>(B, L.deph_deg)[cnt_deph] / (float)A.n_spins_global;
                 cnt_deph++;
             }
             if (mask_ev & EV_GRAD) { // kernels.cu:181-187
@@ -282,10 +327,10 @@ __device__ __noinline__ AdvOut advance_walker(const AdvCtx *cx, const uint32_t p
             if ((mask_ev & EV_ECHO) && scan + 1 == A.n_scans) { // kernels.cu:202-215
                 const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
                 dephase_relax(m, acc, tT1[ts], tT2[ts], dt_s);
-                if (stage) stage[cur_te] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts);
+                if (stage) *g.stage(A, cur_te) = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts);
                 acc = 0.f;
                 t_old = tp;
-                if (A.sums_fx) echo_sums_add(cx->bsum, cur_te * L.n_sub + ts, m);
+                if (A.sums_fx) echo_sums_add(g.bsum + (size_t)g.k_loc * g.n_bsum, cur_te * L.n_sub + ts, m);
                 cur_te++;
             }
             ev++;
@@ -345,14 +390,14 @@ __device__ __noinline__ AdvOut advance_walker(const AdvCtx *cx, const uint32_t p
         flags |= WF_DONE;
         rem = 0;
         if (A.scan_end < A.n_scans) { // pause at a TR boundary: the round index is the whole RNG state
-            A.state_a[cx->st_idx] = make_uint4(p0, p1, p2, r_next);
-            A.state_b[cx->st_idx] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts | ((lost ? 1u : 0u) << 8));
-            A.state_vox[cx->st_idx] = ((p0 >> SC.fb) * A.ny + (p1 >> SC.fb)) * A.nz + (p2 >> SC.fb);
+            A.state_a[g.st_idx(A)] = make_uint4(p0, p1, p2, r_next);
+            A.state_b[g.st_idx(A)] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts | ((lost ? 1u : 0u) << 8));
+            A.state_vox[g.st_idx(A)] = ((p0 >> SC.fb) * A.ny + (p1 >> SC.fb)) * A.nz + (p2 >> SC.fb);
         } else if (stage) {
             // echoes that never fired (beyond the TR, or after the walker was abandoned) read 0, like the reference's zero-initialised
             // outputs (monte_carlo.cu:256,259-260); the final position is the last committed one (kernels.cu:220-221)
-            for (uint32_t e = cur_te; e < A.n_te; e++) stage[e] = make_uint4(0u, 0u, 0u, 0u);
-            if (!RECORD) stage[A.n_te] = make_uint4(__float_as_uint((float)((double)p0 * SC.unit_m[0])), __float_as_uint((float)((double)p1 * SC.unit_m[1])),
+            for (uint32_t e = cur_te; e < A.n_te; e++) *g.stage(A, e) = make_uint4(0u, 0u, 0u, 0u);
+            if (!RECORD) *g.stage(A, A.n_te) = make_uint4(__float_as_uint((float)((double)p0 * SC.unit_m[0])), __float_as_uint((float)((double)p1 * SC.unit_m[1])),
                                                     __float_as_uint((float)((double)p2 * SC.unit_m[2])), lost ? 1u : 0u);
         }
     } else {
@@ -373,66 +418,44 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const BlobLayout &L = A.L;
-    const uint32_t nthr = blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
 
-    // ---- shared memory: [sequence tables] [block sums, int64] [scale constants of this block's scales] [event state] [normals, SHARED] ----
-    const uint8_t *B = A.blob;
-    uint32_t off = 0;
+    // ---- shared memory: [sequence tables] [block sums, int64] [scale constants of this block's scales] [event state] [normals, SHARED];
+    //      which (spin, scale): see Geo ----
+    const Geo<SHARED> g(A, smem);
+    const uint32_t nthr = g.nthr;
+    const uint8_t *B = g.B;
     if (A.blob_in_smem) {
         const uint32_t nw = L.bytes / 4;
         const uint32_t *src = reinterpret_cast<const uint32_t *>(A.blob);
         uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
         for (uint32_t i = threadIdx.x; i < nw; i += nthr) dst[i] = __ldg(src + i);
-        B = smem;
-        off = L.bytes; // multiple of 16
     }
-    const uint32_t n_grp = SHARED ? A.group : 1u;                   // scales walked by this block
-    const uint32_t n_bsum = A.sums_fx ? A.n_te * L.n_sub * 4u : 0u; // entries per scale
-    long long *bsum = reinterpret_cast<long long *>(smem + off);
-    off += (n_bsum * n_grp * 8u + 15u) & ~15u;
-    uint8_t *sct = smem + off;
-    off += A.scale_stride * n_grp;
-    uint32_t *es = reinterpret_cast<uint32_t *>(smem + off) + threadIdx.x; // field f of this thread: es[f * nthr]
-    off += ES_FIELDS * 4u * nthr;                                          // (nthr is a multiple of 32: stays 16-byte aligned)
-    float4 *nbuf = reinterpret_cast<float4 *>(smem + off);                 // [2][kBatch][32], SHARED only
-
-    // ---- which (spin, scale) ----
-    uint32_t k, j, k_loc, k_first;
-    if (SHARED) {
-        k_first = A.k_lo + (blockIdx.x % A.n_groups) * A.group;
-        k_loc = threadIdx.x >> 5;
-        k = k_first + k_loc;
-        j = A.j_first + (blockIdx.x / A.n_groups) * 32u + lane;
-    } else {
-        k_loc = 0u;
-        const uint32_t kn = A.k_hi - A.k_lo;
-        k = k_first = A.k_lo + blockIdx.x % kn;
-        j = A.j_first + (blockIdx.x / kn) * kBlock + threadIdx.x;
-    }
+    const uint32_t n_grp = SHARED ? A.group : 1u; // scales walked by this block
+    const uint32_t n_bsum = g.n_bsum;             // sum entries per scale
+    long long *bsum = g.bsum;
+    uint32_t *es = g.es;   // field f of this thread: es[f * nthr]
+    float4 *nbuf = g.nbuf; // [2][kBatch][32], SHARED only
+    const uint32_t k_first = g.k_first, kc = g.k, j = g.j, jl = g.jl, spin_no = g.spin_no;
     for (uint32_t i = threadIdx.x; i < n_bsum * n_grp; i += nthr) bsum[i] = 0;
     {
         const uint32_t wps = A.scale_stride / 4u; // words per scale record
         const uint32_t *src = reinterpret_cast<const uint32_t *>(A.scale_tab) + (size_t)k_first * wps;
         for (uint32_t i = threadIdx.x; i < wps * n_grp; i += nthr)
-            reinterpret_cast<uint32_t *>(sct)[i] = (k_first + i / wps) < A.k_hi ? __ldg(src + i) : 0u;
+            reinterpret_cast<uint32_t *>(g.sct)[i] = (k_first + i / wps) < A.k_hi ? __ldg(src + i) : 0u;
     }
     __syncthreads();
 
-    const bool spin_ok = j < A.j_end;
-    const bool valid = spin_ok && k < A.k_hi;
-    const uint32_t kc = k < A.k_hi ? k : k_first; // a padding warp of the last group reads valid constants and walks nothing
-    const ScaleConst &SC = *reinterpret_cast<const ScaleConst *>(sct + (size_t)(kc - k_first) * A.scale_stride);
+    const bool valid = g.valid;
+    const ScaleConst &SC = g.sc(A);
     const float *sgt = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(&SC) + SC.sgt_off);
     const uint32_t fb = SC.fb;
 
     const float *gtx = blob_ptr<float>(B, L.gx), *gty = blob_ptr<float>(B, L.gy), *gtz = blob_ptr<float>(B, L.gz);
     const float *tpXY = blob_ptr<float>(B, L.pXY);
-
-    const uint32_t jl = spin_ok ? (A.order ? __ldg(A.order + ((!SHARED && A.order_per_scale) ? (size_t)k * A.n_local : 0) + j) : j) : 0u;
-    const uint32_t spin_no = A.spin_first + jl; // GLOBAL spin id: RNG key and dephasing term
     const uint32_t n0 = A.nx, n1 = A.ny, n2 = A.nz;
-    const size_t st_idx = (size_t)kc * A.n_local + jl;
+    const size_t st_idx = g.st_idx(A);
+    (void)j;
 
     // ---- walker state ----
     uint32_t p0 = 0, p1 = 0, p2 = 0; // fixed-point position
@@ -485,7 +508,6 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
     float sg0 = sgt[3 * ts_of(wcur)], sg1 = sgt[3 * ts_of(wcur) + 1], sg2 = sgt[3 * ts_of(wcur) + 2];
 
     const size_t out_row = (size_t)kc * A.n_local + jl;
-    uint4 *stage = A.stage ? A.stage + out_row * A.stage_row : nullptr;            // [n_te] echoes (Mx, My, Mz, T) + final position
     float *X1 = (RECORD && A.XYZ1) ? A.XYZ1 + out_row * A.trj * 3 : nullptr;       // trajectories go straight to the reference layout
     if (RECORD && X1 && valid && A.scan_first == 0) { // slot 0 starts as the (scaled) initial position (kernels.cu:96)
 #pragma unroll
@@ -574,11 +596,8 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
     };
 
     // ======================================= events =======================================
-    AdvCtx cx;
-    cx.A = &A; cx.B = B; cx.SC = &SC; cx.es = es; cx.bsum = bsum + (size_t)k_loc * n_bsum; cx.stage = stage; cx.st_idx = st_idx;
-    cx.spin_no = spin_no; cx.nthr = nthr; cx.n_bsum = n_bsum;
     auto advance = [&](const uint32_t r_next) { // (see advance_walker)
-        const AdvOut o = advance_walker<STATS, RECORD, VOX, GRUNS>(&cx, p0, p1, p2, wcur, acc, cnt_grad,
+        const AdvOut o = advance_walker<STATS, RECORD, VOX, GRUNS, SHARED>(&A, p0, p1, p2, wcur, acc, cnt_grad,
                                                                   (lost ? WF_LOST : 0u) | (grun ? WF_GRUN : 0u) | (fresh ? WF_FRESH : 0u), r_next);
         acc = o.acc; rem = o.rem; cnt_grad = o.cnt_grad;
         done = (o.flags & WF_DONE) != 0u; grun = (o.flags & WF_GRUN) != 0u;

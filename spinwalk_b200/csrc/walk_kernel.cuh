@@ -93,8 +93,10 @@ struct WalkArgs {
     // Per-spin results go to STAGING ROWS, one per (scale, local spin): n_te echo slots (Mx, My, Mz, tissue) and one slot for the final
     // position, 16 bytes each — a thread's scattered result write is whole aligned 16/32-byte pieces instead of three partial-sector
     // stores into three arrays; unpack_rows_kernel (engine.cu) streams the rows into the reference layouts below.
-    uint4   *stage;          // [K][n_local][stage_row]
+    uint4   *stage;          // [K][stage_chunks][stage_row][32]: per warp-sized chunk of rows, structure of arrays (walk_fast.cuh Geo::stage)
     uint32_t stage_row;      // n_te + 1
+    uint32_t stage_chunks;   // ceil(n_local / 32)
+    int32_t  stage_by_slot;  // rows are indexed by the thread slot (coalesced writes; un-permuted by unpack_rows_kernel), else by the local spin
     float   *XYZ1;           // [K][n_local][trj][3]: written directly only when trajectories are recorded
     unsigned long long *sums_fx; // [K][E][n_sub][4]: sum Mx, My, Mz in fixed point (kSumScale), count
     unsigned long long *counters; // [5]: steps, mask_gathers, field_gathers, rejects, lost
@@ -352,7 +354,9 @@ __global__ void __launch_bounds__(kBlock) walk_compat_kernel(const WalkArgs A)
     bool lost = false;
 
     const size_t out_row = (size_t)k * A.n_local + jl;
-    uint4 *stage = (A.stage && j < A.j_end) ? A.stage + out_row * A.stage_row : nullptr; // echo slots + final position (WalkArgs)
+    // echo slots + final position (WalkArgs::stage): slot e of this walker is stage[e * 32]
+    const uint32_t srow = A.stage_by_slot ? j : jl;
+    uint4 *stage = (A.stage && j < A.j_end) ? A.stage + (((size_t)k * A.stage_chunks + (srow >> 5)) * A.stage_row) * 32u + (srow & 31u) : nullptr;
     float *X1 = (A.record && A.XYZ1) ? A.XYZ1 + out_row * A.trj * 3 : nullptr;
     if (X1 && alive) { // slot 0 starts as the (scaled) initial position (kernels.cu:96)
         X1[0] = xyz_f[0]; X1[1] = xyz_f[1]; X1[2] = xyz_f[2];
@@ -484,11 +488,11 @@ __global__ void __launch_bounds__(kBlock) walk_compat_kernel(const WalkArgs A)
                 if (alive) {
                     const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
                     dephase_relax(m, acc, T1, T2, dt_s);
-                    if (stage) stage[cur_te] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts_old);
+                    if (stage) stage[cur_te * 32u] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts_old);
                     acc = 0.f;
                     t_old = tp;
                     if (A.sums_fx) echo_sums_add(bsum, cur_te * L.n_sub + ts_old, m);
-                } else if (stage) stage[cur_te] = make_uint4(0u, 0u, 0u, 0u); // abandoned spin: unwritten echoes read 0 (monte_carlo.cu:256,259-260)
+                } else if (stage) stage[cur_te * 32u] = make_uint4(0u, 0u, 0u, 0u); // abandoned spin: unwritten echoes read 0 (monte_carlo.cu:256,259-260)
                 cur_te++;
             }
         }
@@ -502,8 +506,8 @@ __global__ void __launch_bounds__(kBlock) walk_compat_kernel(const WalkArgs A)
 
     // ---- final position (kernels.cu:220-221 leaves the last committed position in xyz1); echoes that never fired read 0 ----
     if (stage) {
-        for (uint32_t e = echoes_done; e < A.n_te; e++) stage[e] = make_uint4(0u, 0u, 0u, 0u);
-        if (!A.record) stage[A.n_te] = make_uint4(__float_as_uint((float)px[0]), __float_as_uint((float)px[1]), __float_as_uint((float)px[2]), lost ? 1u : 0u);
+        for (uint32_t e = echoes_done; e < A.n_te; e++) stage[e * 32u] = make_uint4(0u, 0u, 0u, 0u);
+        if (!A.record) stage[A.n_te * 32u] = make_uint4(__float_as_uint((float)px[0]), __float_as_uint((float)px[1]), __float_as_uint((float)px[2]), lost ? 1u : 0u);
     }
 
     // ---- flush block sums and counters ----
