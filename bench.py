@@ -536,8 +536,13 @@ def main():
     if not args.no_e2e:
         e2e = W.e2e(H, mode, per_spin_out, args.steps)
 
-    # ---- roofline of the walk kernel: algorithmic bytes / mean launch duration
+    # ---- roofline of the walk kernel: algorithmic bytes / mean launch duration; and the voxel fetch against its own ceiling
     roofline = W.roofline(H, counts, T, args.steps, per_spin_out, peak, peak_src, mode, args)
+    if mode == sw.MODE_FAST and K >= 10 and cfg_kw["scale_type"] == 0 and not args.no_extras:
+        try:
+            roofline["gather"] = W.gather_roofline(H, mode)
+        except Exception as ex:  # a diagnostic must never cost the bench line
+            roofline["gather"] = {"error": str(ex)}
 
     line = {"metric": "spin-steps/s", "value": value, "unit": "spin-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": T["dev_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -713,8 +718,9 @@ class Walk:
         per_pass_bytes = (counts["mask_gathers"] * (4 if H["eng"].has_fieldmap else 1)) * steps_scale + S * K * (24 + ((13 * E + 12) if per_spin_out else 0))
         ker_ms = T["ker_ms"] / steps
         achieved = per_pass_bytes / (ker_ms * 1e-3) / 1e9
-        traffic, traffic_src = stamped_traffic(f"{H['name']}:{args.mode}{'' if H['slab'] else ':full'}", S)
+        traffic, traffic_src, ncu_launches = stamped_traffic(f"{H['name']}:{args.mode}{'' if H['slab'] else ':full'}", S)
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "ncu_launches": ncu_launches,
                 "peak_source": peak_src, "kernel": "swk::walk_fast_kernel" if mode == sw.MODE_FAST else "swk::walk_compat_kernel",
                 "algorithmic_bytes_per_launch": per_pass_bytes, "kernel_ms_per_launch": ker_ms, "bytes_per_spin_step": per_pass_bytes / H["steps_per_pass"],
                 "attempts_with_voxel_change_per_step": counts["mask_gathers"] * steps_scale / max(1, H["steps_per_pass"]),
@@ -749,8 +755,11 @@ class Walk:
         walk = c["mask_gathers"] / (t["ker_ms"] / 2 * 1e-3)
         return {"scales": [small[0], small[-1]], "walk_gathers_per_s": walk, "probe_gathers_per_s": probe["gathers_per_s"], "table_bytes": probe["table_bytes"],
                 "frac": walk / probe["gathers_per_s"], "kernel_ms": t["ker_ms"] / 2,
-                "note": "probe = swk_probe_gather: dependent random 4-byte gathers over the same voxel table with the walk's load instruction and nothing else "
-                        "(HBM row-activation bound, DESIGN.md §5); walk = attempts whose voxel changed (STATS kernel variant) / kernel time of the same scales"}
+                "note": "the walk against the random-gather probe on the SAME voxel table, on the 10 smallest FoV scales only: there every attempt lands in a voxel far "
+                        "from the last one (sigma >= 4 voxels), so both count the same kind of access.  probe = swk_probe_gather: dependent random 4-byte gathers with "
+                        "the walk's load instruction and nothing else — a cache-resident table (z slab) is bound by the L1TEX tag rate (one 128-byte line per clock and SM "
+                        "for a fully divergent warp load: 291 G/s), a table in HBM by row activations (DESIGN.md §5); walk = attempts whose voxel changed (STATS kernel "
+                        "variant) / kernel time of the same scales"}
 
     def extra_full_table(self, peak, peak_src, args):
         """the headline workload on the FULL [nx][ny][nz] voxel table (SWK_RUN_NO_ZSLAB): what a phantom without an invariant axis costs, and the
@@ -884,13 +893,14 @@ def stamped_traffic(key, spins_per_gpu):
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
-        return None, "no capture (profiles/traffic.json missing)"
+        return None, "no capture (profiles/traffic.json missing)", None
     ent = tj.get(key)
     if not ent:
-        return None, f"no capture for {key}"
+        return None, f"no capture for {key}", None
     if ent.get("kernel_stamp") != source_stamp():
-        return None, f"stale capture refused: taken on kernel sources {ent.get('kernel_stamp')}, this build is {source_stamp()}"
-    return ent["dram_bytes_per_launch"] * (spins_per_gpu / ent["spins_per_gpu"]), ent["source"]
+        return None, f"stale capture refused: taken on kernel sources {ent.get('kernel_stamp')}, this build is {source_stamp()}", None
+    # per walk launch of the pass: issue-slot utilisation, active lanes per instruction, cache hit rates (what bounds a cache-resident table)
+    return ent["dram_bytes_per_launch"] * (spins_per_gpu / ent["spins_per_gpu"]), ent["source"], ent.get("launches")
 
 
 if __name__ == "__main__":

@@ -188,7 +188,7 @@ void swk_free_pinned(void *ptr);
 
 /* ---- diagnostics: the roofline of the voxel fetch, measured on THIS device and THIS phantom ----
  * Launches a kernel that does nothing but dependent 4-byte gathers at uniformly random addresses of the engine's voxel
- * table (the packed words when they exist, else the fieldmap, else the mask read as words) with the walk's load
+ * table (the one the last run walked: the z slab, else the packed words when they exist, else the fieldmap, else the mask read as words) with the walk's load
  * instruction, `threads_per_sm` resident threads per SM and `iters` gathers per thread, and reports gathers/s
  * (CUDA events on the engine stream).  What the walk can reach at small FoV scales, where every step lands in a
  * voxel far from the last one.  Not part of the reference (it has no profiling hooks). */

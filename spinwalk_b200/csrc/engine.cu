@@ -62,6 +62,7 @@ struct swk_engine {
     bool packed_valid = false;
     DevBuf slab;            // SWK_RUN_ZSLAB: packed words of one z plane, [nx][ny]
     bool slab_valid = false;
+    bool last_used_slab = false; // the last run walked the z slab: swk_probe_gather probes that table
     int z_invariant = -1;   // -1 not checked yet, 0 / 1: mask and field map do not depend on z
     uint64_t dims[3] = {0, 0, 0};
     float fov[3] = {0, 0, 0};
@@ -1199,6 +1200,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     CK(cudaEventElapsedTime(&ms_all, e->evA, e->ev1));
 
     e->n_scales = n_scales;
+    e->last_used_slab = use_slab;
     e->out_flags = flags;
     e->last_sums = (E * ns) ? sums : nullptr;
     e->last_slices = n_slices;
@@ -1316,7 +1318,7 @@ int swk_probe_gather(swk_engine *e, uint32_t threads_per_sm, uint32_t iters, dou
     if (!e->has_phantom) return fail(e, SWK_ERR_STATE, "swk_probe_gather: no phantom (swk_set_phantom)");
     if (iters == 0 || threads_per_sm == 0) return fail(e, SWK_ERR_INVALID, "swk_probe_gather: iters and threads_per_sm must be positive");
     CK(cudaSetDevice(e->device));
-    const DevBuf &t = (e->packed_valid && e->packed.p) ? e->packed : (e->fieldmap.p ? e->fieldmap : e->mask);
+    const DevBuf &t = (e->last_used_slab && e->slab_valid) ? e->slab : ((e->packed_valid && e->packed.p) ? e->packed : (e->fieldmap.p ? e->fieldmap : e->mask));
     const uint32_t n_words = (uint32_t)std::min<size_t>(t.bytes / 4, 0xffffffffu);
     if (n_words == 0) return fail(e, SWK_ERR_STATE, "swk_probe_gather: voxel table is empty");
     int rc;
