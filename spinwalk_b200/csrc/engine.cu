@@ -60,6 +60,7 @@ struct swk_engine {
     // phantom
     DevBuf mask, fieldmap, packed;
     bool packed_valid = false;
+    bool packed_brick = false; // layout of `packed`: 2 x 2 x 4 bricks instead of row-major
     DevBuf slab;            // SWK_RUN_ZSLAB: packed words of one z plane, [nx][ny]
     bool slab_valid = false;
     bool last_used_slab = false; // the last run walked the z slab: swk_probe_gather probes that table
@@ -191,6 +192,16 @@ __device__ __forceinline__ uint32_t pack_word(float field, uint32_t ts)
 __global__ void pack_voxels_kernel(const uint8_t *mask, const float *field, size_t n, uint32_t *out)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = pack_word(field[i], mask[i]);
+}
+// ... in bricks of 2 x 2 x 4 voxels (16 words = one 64-byte fetch unit; walk_fast.cuh table_index); padding words of odd sizes are never read
+__global__ void pack_bricks_kernel(const uint8_t *mask, const float *field, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t *out)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    const uint32_t bry = (ny + 1u) >> 1, brz = (nz + 3u) >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t z = (uint32_t)(i % nz), y = (uint32_t)((i / nz) % ny), x = (uint32_t)(i / ((size_t)nz * ny));
+        out[(((((size_t)(x >> 1) * bry + (y >> 1)) * brz + (z >> 2)) << 4) | ((x & 1u) << 3) | ((y & 1u) << 2) | (z & 3u))] = pack_word(field[i], mask[i]);
+    }
 }
 
 // z-slab table: does any voxel differ from the z = 0 voxel of its column?  (one streaming pass over mask and field map)
@@ -411,6 +422,7 @@ int swk_create(int device_id, swk_engine **out)
     e->sm_count = prop.multiProcessorCount;
     e->smem_optin = prop.sharedMemPerBlockOptin;
     e->mem_pitch = prop.memPitch;
+    if (const char *ev = getenv("SWK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(ev)); // experiment (profiles/README.md): 32 / 64 / 128
     if (const char *ev = getenv("SWK_MEMPITCH")) e->mem_pitch = (size_t)strtoull(ev, nullptr, 10); // test hook: exercise the per-scale copies
     *out = e;
     return SWK_OK;
@@ -845,13 +857,21 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             use_slab = true;
         }
     }
-    if (want_packed && !use_slab && !e->packed_valid) {
+    const bool want_brick = getenv("SWK_BRICK") != nullptr && atoi(getenv("SWK_BRICK")) != 0; // experiment (profiles/README.md): 2 x 2 x 4 bricks
+    if (want_packed && !use_slab && (!e->packed_valid || e->packed_brick != want_brick)) {
         const size_t V = (size_t)(e->dims[0] * e->dims[1] * e->dims[2]);
-        if ((rc = ensure(e, e->packed, V * sizeof(uint32_t))) != SWK_OK) return rc;
-        pack_voxels_kernel<<<e->sm_count * 16, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), static_cast<const float *>(e->fieldmap.p), V,
-                                                                  static_cast<uint32_t *>(e->packed.p));
+        const size_t words = want_brick ? (size_t)((e->dims[0] + 1) / 2) * ((e->dims[1] + 1) / 2) * ((e->dims[2] + 3) / 4) * 16 : V;
+        if (words >= (1ull << 32)) return fail(e, SWK_ERR_INVALID, "SWK_MODE_FAST indexes voxels with 32 bits: phantom too large");
+        if ((rc = ensure(e, e->packed, words * sizeof(uint32_t))) != SWK_OK) return rc;
+        if (want_brick)
+            pack_bricks_kernel<<<e->sm_count * 16, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), static_cast<const float *>(e->fieldmap.p), (uint32_t)e->dims[0],
+                                                                      (uint32_t)e->dims[1], (uint32_t)e->dims[2], static_cast<uint32_t *>(e->packed.p));
+        else
+            pack_voxels_kernel<<<e->sm_count * 16, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), static_cast<const float *>(e->fieldmap.p), V,
+                                                                      static_cast<uint32_t *>(e->packed.p));
         CK(cudaGetLastError());
         e->packed_valid = true;
+        e->packed_brick = want_brick;
         extra_launches++;
     }
 
@@ -859,6 +879,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     A.mask = static_cast<const uint8_t *>(e->mask.p);
     A.fieldmap = static_cast<const float *>(e->fieldmap.p);
     A.packed = want_packed ? static_cast<const uint32_t *>(use_slab ? e->slab.p : e->packed.p) : nullptr;
+    A.brick = (want_packed && !use_slab && e->packed_brick) ? 1 : 0;
     A.nx = (uint32_t)e->dims[0]; A.ny = (uint32_t)e->dims[1]; A.nz = (uint32_t)e->dims[2];
     A.V = (int64_t)(e->dims[0] * e->dims[1] * e->dims[2]);
     for (int i = 0; i < 3; i++) A.fov[i] = e->fov[i];

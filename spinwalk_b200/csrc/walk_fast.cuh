@@ -490,7 +490,15 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
     // current voxel: table index, substrate, field.  The reference loads field / T1 / T2 at the first accepted step
     // (kernels.cu:91,150-170); holding the field of the CURRENT voxel from the start is equivalent: a first step that stays in
     // the voxel reads this very value.
-    uint32_t idx_cur = VOX == VOX_SLAB ? (p0 >> fb) * n1 + (p1 >> fb) : ((p0 >> fb) * n1 + (p1 >> fb)) * n2 + (p2 >> fb);
+    // index of a voxel in the table that is walked: the [nx][ny] slab, the row-major volume, or (packed words, A.brick) the volume cut into bricks
+    // of 2 x 2 x 4 voxels = one 64-byte fetch unit each, so that a step of a fraction of a voxel along ANY axis mostly stays inside the line it has
+    const uint32_t bry = A.brick ? (n1 + 1u) >> 1 : 0u, brz = A.brick ? (n2 + 3u) >> 2 : 0u;
+    auto table_index = [&](const uint32_t v0, const uint32_t v1, const uint32_t v2) -> uint32_t {
+        if (VOX == VOX_SLAB) return v0 * n1 + v1;
+        if (VOX == VOX_PACKED && A.brick) return ((((v0 >> 1) * bry + (v1 >> 1)) * brz + (v2 >> 2)) << 4) | ((v0 & 1u) << 3) | ((v1 & 1u) << 2) | (v2 & 3u);
+        return (v0 * n1 + v1) * n2 + v2;
+    };
+    uint32_t idx_cur = table_index(p0 >> fb, p1 >> fb, p2 >> fb);
     uint32_t ind3_cur = ((p0 >> fb) * n1 + (p1 >> fb)) * n2 + (p2 >> fb); // STATS only
     uint32_t wcur = 0;   // PACKED / SLAB: the packed word; MASK / SPLIT: the substrate id
     float fcur = 0.f;    // SPLIT: field of the current voxel (Tesla)
@@ -540,7 +548,7 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
             if (v1 >= n1) { q1 = fov_boundary(q1, p1, n1, fb, A.cross_fov); v1 = q1 >> fb; }
             if (v2 >= n2) { q2 = fov_boundary(q2, p2, n2, fb, A.cross_fov); v2 = q2 >> fb; }
         }
-        const uint32_t idx = VOX == VOX_SLAB ? v0 * n1 + v1 : (v0 * n1 + v1) * n2 + v2;
+        const uint32_t idx = table_index(v0, v1, v2);
         uint32_t w = wcur;
         float fv = fcur;
         if (act & (idx != idx_cur)) { // the voxel changed: one gather

@@ -51,7 +51,8 @@ struct WalkArgs {
     // phantom
     const uint8_t *mask;
     const float   *fieldmap; // Tesla at 1 T, or nullptr
-    const uint32_t *packed;  // FAST mode: (field bits & ~15) | substrate, or nullptr
+    const uint32_t *packed;  // FAST mode: packed voxel words (engine.cu pack_word), or nullptr
+    int32_t  brick;          // the packed volume is stored in 2 x 2 x 4 bricks (walk_fast.cuh table_index)
     uint32_t nx, ny, nz;
     int64_t  V;
     float    fov[3];         // metres (held as float like the reference, monte_carlo.cuh:37)
