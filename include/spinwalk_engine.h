@@ -157,8 +157,15 @@ enum { SWK_OUT_M1 = 1, SWK_OUT_XYZ1 = 2, SWK_OUT_T = 4, SWK_OUT_ALL = 7,
                               device; every cylinder phantom of `spinwalk phantom -c`) is walked on the packed voxel words of ONE z plane — the
                               same words, hence the same results bit for bit, from an L1/L2-resident [nx][ny] table instead of [nx][ny][nz].
                               This flag (or environment SWK_NO_ZSLAB=1) keeps the full table: A/B tests, the gather-roofline measurement. */
-       SWK_RUN_NO_SHARE = 1024 /* FAST mode: every thread generates its own normals (the PRIVATE kernel variant) even when several scales could
-                              share one generation per spin (walk_fast.cuh); same results bit for bit; for A/B tests (also: SWK_NO_SHARE=1) */ };
+       SWK_RUN_NO_SHARE = 1024, /* FAST mode: every thread generates its own normals (the PRIVATE kernel variant) even when several scales could
+                              share one generation per spin (walk_fast.cuh); same results bit for bit; for A/B tests (also: SWK_NO_SHARE=1) */
+       SWK_RUN_NO_ONEWALK = 2048 /* FAST mode: when the scales act on the gradients or on the phase cycling (WHAT_TO_SCALE 1, 2) every scale of a spin
+                              walks the same path (the reference re-seeds seed+spin per scale, kernels.cu:77-88, and the FoV is not scaled), so by
+                              default ONE walker per spin carries the magnetisation of every scale: the walk is paid once instead of n_scales
+                              times, positions and tissues are bit-identical, magnetisations agree to FP32 round-off (the gradient phase is
+                              scaled after the sum instead of term by term).  swk_stats then counts every step / gather / rejection n_scales
+                              times (the statistics of the walks it stands for).  Not used while trajectories are recorded.  This flag (or
+                              SWK_NO_ONEWALK=1) walks every scale separately: A/B tests. */ };
 int swk_run_device(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags,
                    double *d_sums);
 

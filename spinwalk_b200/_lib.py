@@ -12,7 +12,7 @@ SWK_OK, SWK_ERR_INVALID, SWK_ERR_CUDA, SWK_ERR_MEMORY, SWK_ERR_STATE, SWK_ERR_SU
 SCALE_FOV, SCALE_GRADIENT, SCALE_PHASE_CYCLING = 0, 1, 2
 MODE_COMPAT, MODE_FAST = 0, 1
 OUT_M1, OUT_XYZ1, OUT_T, OUT_ALL, RUN_STATS, RUN_NO_SORT, RUN_NO_PACK, RUN_NO_REBIN = 1, 2, 4, 7, 16, 32, 64, 128
-RUN_ZSLAB, RUN_NO_ZSLAB, RUN_NO_SHARE = 256, 512, 1024
+RUN_ZSLAB, RUN_NO_ZSLAB, RUN_NO_SHARE, RUN_NO_ONEWALK = 256, 512, 1024, 2048
 
 
 class Params(C.Structure):  # struct swk_params

@@ -81,6 +81,7 @@ struct swk_engine {
     // spins
     DevBuf xyz0, m0, order, inv_order; // inv_order: spin -> thread slot (unpack_rows_kernel)
     DevBuf state_a, state_b, state_vox;                     // re-binning pauses of long runs: per (scale, spin) walker state
+    DevBuf mstate;                                          // one walk for all scales (walk_fast.cuh MULTI): magnetisation per (scale, thread slot)
     DevBuf sort_keys_in, sort_keys_out, sort_ids, sort_tmp; // kept between runs: re-sorting after every swk_set_spins must not malloc
     bool order_valid = false;
     uint32_t order_slice = 0; // slice length the order was built for (0 = one slice)
@@ -433,7 +434,7 @@ void swk_destroy(swk_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     for (DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
+                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->mstate, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
         release(*b);
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -724,6 +725,15 @@ static walk_fn pick_fast(int vox, bool gruns, bool record, bool stats)
 #undef SWK_PICK
 #undef SWK_PICK2
 }
+// one walk for all gradient / phase-cycling scales (walk_fast.cuh MULTI): PRIVATE geometry, no trajectory recording
+static walk_fn pick_fast_multi(int vox, bool gruns, bool stats)
+{
+#define SWK_PICK2(V, G) (stats ? walk_fast_kernel<true, false, V, G, false, true> : walk_fast_kernel<false, false, V, G, false, true>)
+#define SWK_PICK(V) (gruns ? SWK_PICK2(V, true) : SWK_PICK2(V, false))
+    return vox == VOX_PACKED ? SWK_PICK(VOX_PACKED) : (vox == VOX_SLAB ? SWK_PICK(VOX_SLAB) : (vox == VOX_SPLIT ? SWK_PICK(VOX_SPLIT) : SWK_PICK(VOX_MASK)));
+#undef SWK_PICK
+#undef SWK_PICK2
+}
 
 static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int scale_type, int mode, int flags, double *d_sums,
                     uint32_t n_slices, const HostOut *host)
@@ -938,6 +948,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     };
     std::vector<Part> parts;
     walk_fn kern_private = nullptr; // FAST: the variant of legs resumed after a re-binning pause (walkers resume at their own rounds)
+    bool onewalk = false;           // FAST: one walker per spin for all (gradient / phase-cycling) scales
     size_t smem_private = 0;
     const size_t bsum_bytes = A.sums_fx ? E * ns * 4 * sizeof(long long) : 0;
     if (mode == SWK_MODE_COMPAT) {
@@ -990,6 +1001,16 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         }
         const size_t fixed_private = ((bsum_bytes + 15) & ~size_t(15)) + stride + (size_t)ES_FIELDS * 4 * kBlock;
         if (fixed_private > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
+        // ONE WALK FOR ALL SCALES (walk_fast.cuh MULTI): gradient and phase-cycling scales do not change the walk, and the reference replays the same
+        // random stream for every scale of a spin (kernels.cu:77-88), so one walker per spin carries the magnetisation of every scale (A.mstate).
+        const size_t fixed_multi = ((bsum_bytes * K + 15) & ~size_t(15)) + stride + (size_t)ES_FIELDS * 4 * kBlock;
+        onewalk = scale_type != SWK_SCALE_FOV && K > 1 && !record && !(flags & SWK_RUN_NO_ONEWALK) && getenv("SWK_NO_ONEWALK") == nullptr &&
+                  fixed_multi <= smem_cap;
+        if (onewalk) {
+            if ((rc = ensure(e, e->mstate, K * S * sizeof(uint4))) != SWK_OK) return rc;
+            A.n_multi = (uint32_t)K;
+            A.mstate = static_cast<uint4 *>(e->mstate.p);
+        }
         // SHARED variant (walk_fast.cuh): 32 spins x G scales per block share the spins' normals: ~45 instead of ~90 instructions per attempt
         // where the launch is issue bound.  Where every attempt fetches a voxel far from the last one (step sigma above ~1 voxel: the small FoV
         // scales) the walk is bound by the gather pipeline instead, the lockstep of a block's scales only costs, and the PRIVATE variant is
@@ -1047,11 +1068,20 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             if (e->L.bytes + p.fixed > smem_cap) A.blob_in_smem = 0;
             parts.push_back(p);
         };
-        add_part(0, cut, want_shared[0] != 0);
-        if (cut < n_scales) add_part(cut, n_scales, want_shared[cut] != 0);
-        if (parts.size() == 2 && !parts[0].shared && !parts[1].shared) { // (e.g. too few scales on the shared side)
-            parts[0].k_hi = n_scales;
-            parts.pop_back();
+        if (onewalk) { // one launch: a block = kBlock spins, geometry of a single scale
+            Part p{};
+            p.k_lo = 0; p.k_hi = 1; p.block = (unsigned)kBlock;
+            p.fixed = fixed_multi;
+            p.kern = pick_fast_multi(vox, gruns, stats_on);
+            if (e->L.bytes + p.fixed > smem_cap) A.blob_in_smem = 0;
+            parts.push_back(p);
+        } else {
+            add_part(0, cut, want_shared[0] != 0);
+            if (cut < n_scales) add_part(cut, n_scales, want_shared[cut] != 0);
+            if (parts.size() == 2 && !parts[0].shared && !parts[1].shared) { // (e.g. too few scales on the shared side)
+                parts[0].k_hi = n_scales;
+                parts.pop_back();
+            }
         }
         for (Part &p : parts) {
             p.smem = (A.blob_in_smem ? e->L.bytes : 0) + p.fixed;
@@ -1122,7 +1152,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         // table at random whatever the order and are not re-binned; a z-slab table is cache resident whatever the order.
         uint32_t scans_per_leg = A.n_scans;
         bool per_scale = false;
-        if (mode == SWK_MODE_FAST && A.order && !A.record && !(flags & SWK_RUN_NO_REBIN) && A.n_scans > 1) {
+        if (mode == SWK_MODE_FAST && A.order && !A.record && !(flags & SWK_RUN_NO_REBIN) && A.n_scans > 1 && !onewalk) { // (a MULTI walk is never paused)
             double sig_vox = 0.;
             const double *sig = reinterpret_cast<const double *>(e->blob_h.data() + e->L.sigma);
             for (uint32_t k = 0; k < n_scales; k++)
@@ -1383,7 +1413,7 @@ uint64_t swk_device_bytes(const swk_engine *e)
     if (!e) return 0;
     uint64_t n = 0;
     for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
+                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->mstate, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
         n += b->bytes;
     return n;
 }

@@ -22,10 +22,15 @@
 //   * 32-bit voxel indices (V < 2^32); ensemble sums in integer fixed point (bit-reproducible, order independent).
 #pragma once
 
+#include <type_traits>
+
 #include "walk_kernel.cuh"
 
 #ifndef SWK_FAST_MIN_BLOCKS
 #define SWK_FAST_MIN_BLOCKS 5 // PRIVATE variant: 48 registers, 40 warps per SM
+#endif
+#ifndef SWK_FAST_MULTI_MINB
+#define SWK_FAST_MULTI_MINB 4  // MULTI variant (one walker per spin for all gradient / phase-cycling scales): 64 registers, 32 warps per SM
 #endif
 #ifndef SWK_FAST_SHARED_MAXT
 #define SWK_FAST_SHARED_MAXT 320 // SHARED variant: at most 10 scales (warps) per block
@@ -204,7 +209,7 @@ enum : uint32_t { ES_M0 = 0u, ES_M1, ES_M2, ES_SCAN, ES_EV, ES_SEG, ES_TSTOP, ES
 // ======================================= events (out of line) =======================================
 // Where a thread's walker lives: scale, thread slot, spin, shared-memory regions.  A pure function of the launch parameters and the
 // thread / block indices, so the out-of-line event code recomputes it instead of receiving a context through local memory.
-template <bool SHARED>
+template <bool SHARED, bool MULTI = false>
 struct Geo {
     uint32_t k, k_first, k_loc, j, jl, spin_no, nthr, n_bsum;
     bool spin_ok, valid;
@@ -218,10 +223,11 @@ struct Geo {
         nthr = blockDim.x;
         uint32_t off = A.blob_in_smem ? A.L.bytes : 0u; // (multiple of 16)
         B = A.blob_in_smem ? smem : A.blob;
-        const uint32_t n_grp = SHARED ? A.group : 1u;
+        const uint32_t n_grp = SHARED ? A.group : 1u;                       // scales walked by this block (scale constants)
+        const uint32_t n_acc = MULTI ? A.n_multi : n_grp;                   // scales this block accumulates sums for (MULTI: all of the run)
         n_bsum = A.sums_fx ? A.n_te * A.L.n_sub * 4u : 0u;
         bsum = reinterpret_cast<long long *>(smem + off);
-        off += (n_bsum * n_grp * 8u + 15u) & ~15u;
+        off += (n_bsum * n_acc * 8u + 15u) & ~15u;
         sct = smem + off;
         off += A.scale_stride * n_grp;
         es = reinterpret_cast<uint32_t *>(smem + off) + threadIdx.x;
@@ -249,10 +255,11 @@ struct Geo {
     // staging slot e of this walker: rows are laid out per warp-sized chunk of thread slots, structure of arrays — [scale][chunk][slot e][lane] — so a
     // warp's echo write is 512 contiguous bytes.  Indexed by the thread slot (coalesced; unpack_rows_kernel un-permutes through the inverse order)
     // or, for the legs of a re-binned run whose order changes, by the spin.
-    __device__ __forceinline__ uint4 *stage(const WalkArgs &A, uint32_t e) const
+    __device__ __forceinline__ uint4 *stage(const WalkArgs &A, uint32_t e) const { return stage(A, e, k); }
+    __device__ __forceinline__ uint4 *stage(const WalkArgs &A, uint32_t e, uint32_t kk) const
     {
         const uint32_t row = A.stage_by_slot ? j : jl;
-        return A.stage + (((size_t)k * A.stage_chunks + (row >> 5)) * A.stage_row + e) * 32u + (row & 31u);
+        return A.stage + (((size_t)kk * A.stage_chunks + (row >> 5)) * A.stage_row + e) * 32u + (row & 31u);
     }
 };
 
@@ -260,6 +267,9 @@ struct AdvOut {
     float acc;
     int rem;
     uint32_t cnt_grad, flags;
+};
+struct AdvOutMulti : AdvOut {
+    float accg; // MULTI: phase accrued from the UNSCALED gradients since the last event
 };
 enum : uint32_t { WF_LOST = 1u, WF_DONE = 2u, WF_GRUN = 4u, WF_FRESH = 8u };
 
@@ -410,10 +420,190 @@ __device__ __noinline__ AdvOut advance_walker(const WalkArgs *pA, const uint32_t
     return o;
 }
 
+// advance_walker for MULTI kernels (one walk for all scales, WalkArgs::n_multi).  The same segment machine as advance_walker above — kept as a
+// second function so that the code of the tuned single-scale variants stays exactly what it was (ptxas allocates the registers of a kernel and its
+// out-of-line callee together: restructuring the callee moved spills into the round loop of the PRIVATE variant).
+// MULTI: the walker stands for the same spin at every scale of a run whose scales act on the
+// gradients or on the phase cycling (monte_carlo.cu:288-290, 303) — their walks are identical, only the accrued phase differs, and it is linear in
+// the gradient scale: phase_k = acc + gscale_k * accg with acc = field + dephasing terms and accg = the gradient term of the UNSCALED gradients.
+// Every event is applied to the magnetisation of each scale in turn (A.mstate, coalesced 16-byte slots); the walk itself is paid once.
+template <bool STATS, int VOX, bool GRUNS>
+__device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, const uint32_t p0, const uint32_t p1, const uint32_t p2, const uint32_t wcur, float acc,
+                                                         float accg, uint32_t cnt_grad, uint32_t flags, const uint32_t r_next)
+{
+    constexpr bool MULTI = true, SHARED = false, RECORD = false;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const WalkArgs &A = *pA;
+    const BlobLayout &L = A.L;
+    const Geo<SHARED, MULTI> g(A, smem);
+    const uint8_t *B = g.B;
+    const ScaleConst &SC = g.sc(A);
+    uint32_t *es = g.es;
+    const uint32_t nthr = g.nthr;
+    const bool stage = A.stage != nullptr;
+    const uint32_t n_tp = A.n_tp;
+    const int32_t  *tl_time = blob_ptr<int32_t>(B, L.tl_time);
+    const uint32_t *tl_mask = blob_ptr<uint32_t>(B, L.tl_mask), *tl_run = blob_ptr<uint32_t>(B, L.tl_run);
+    const float *gtx = blob_ptr<float>(B, L.gx), *gty = blob_ptr<float>(B, L.gy), *gtz = blob_ptr<float>(B, L.gz);
+    const float *tT1 = blob_ptr<float>(B, L.T1s), *tT2 = blob_ptr<float>(B, L.T2s);
+    const uint32_t ts = (VOX == VOX_PACKED || VOX == VOX_SLAB) ? (wcur & 15u) : wcur; // the substrate does not change during events
+    const bool lost = (flags & WF_LOST) != 0u;
+
+    float m[3] = {0.f, 0.f, 0.f};
+    if (!MULTI) { m[0] = __uint_as_float(es[ES_M0 * nthr]); m[1] = __uint_as_float(es[ES_M1 * nthr]); m[2] = __uint_as_float(es[ES_M2 * nthr]); }
+    // fn(scale, magnetisation, gradient scale, linear phase cycling) for this walker's scale — MULTI: for every scale of the run in turn
+    auto each_scale = [&](auto &&fn) {
+        if (MULTI) {
+            for (uint32_t kk = 0; kk < A.n_multi; kk++) {
+                uint4 *slot = A.mstate + (size_t)kk * A.n_local + g.j;
+                const uint4 v = *slot;
+                float mm[3] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z)};
+                const ScaleConst *sk = reinterpret_cast<const ScaleConst *>(A.scale_tab + (size_t)kk * A.scale_stride);
+                fn(kk, kk, mm, __ldg(&sk->gscale), __ldg(&sk->lin_pc));
+                *slot = make_uint4(__float_as_uint(mm[0]), __float_as_uint(mm[1]), __float_as_uint(mm[2]), 0u);
+            }
+        } else fn(g.k, g.k_loc, m, SC.gscale, SC.lin_pc);
+    };
+    uint32_t scan = es[ES_SCAN * nthr], ev = es[ES_EV * nthr], seg = es[ES_SEG * nthr], t_stop = es[ES_TSTOP * nthr], t_old = es[ES_TOLD * nthr];
+    uint32_t cur_rf = es[ES_RF * nthr], cur_te = es[ES_TE * nthr], cnt_deph = es[ES_DEPH * nthr], grad_first = es[ES_GFIRST * nthr], run_len = es[ES_RUNLEN * nthr];
+    const float gscale = MULTI ? 1.f : SC.gscale;
+    int rem = 0;
+    bool finished = false;
+    for (;;) {
+        if (lost) { // abandoned (kernels.cu:155-159)
+            if (scan + 1 != A.n_scans) cur_te = 0; // no echo of the last scan was written
+            finished = true;
+            break;
+        }
+        if (seg == SEG_EVENT) { // events of timepoint tl_time[ev], in the reference's order (kernels.cu:175-215)
+            const uint32_t mask_ev = tl_mask[ev];
+            const uint32_t tp = (uint32_t)tl_time[ev];
+            if (mask_ev & EV_DEPH) { // kernels.cu:175-178
+                acc += (float)g.spin_no * blob_ptr<float>(B, L.deph_deg)[cnt_deph] / (float)A.n_spins_global;
+                cnt_deph++;
+            }
+            if (mask_ev & EV_GRAD) { // kernels.cu:181-187
+                const float Gx = __fmul_rn(gtx[cnt_grad], gscale), Gy = __fmul_rn(gty[cnt_grad], gscale), Gz = __fmul_rn(gtz[cnt_grad], gscale); // monte_carlo.cu:288-290
+                const double X = (double)p0 * SC.unit_m[0], Y = (double)p1 * SC.unit_m[1], Z = (double)p2 * SC.unit_m[2];
+                double gp = __fma_rn((double)Gz, Z, __fma_rn((double)Gx, X, __dmul_rn((double)Gy, Y)));
+                gp = gp * 1e-3 * (double)A.timestep_us * 1e-6 * kGamma;
+                if (MULTI) accg = (float)__fma_rn(gp, kRad2Deg, (double)accg);
+                else acc = (float)__fma_rn(gp, kRad2Deg, (double)acc);
+                cnt_grad++;
+            }
+            if (mask_ev & EV_RF) { // kernels.cu:190-199
+                const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
+                const float rs = blob_ptr<float>(B, L.rf_s)[cur_rf], rc = blob_ptr<float>(B, L.rf_c)[cur_rf], rp = blob_ptr<float>(B, L.rf_ph)[cur_rf];
+                each_scale([&](uint32_t, uint32_t, float *mm, const float gs, float) {
+                    dephase_relax(mm, MULTI ? fmaf(gs, accg, acc) : acc, tT1[ts], tT2[ts], dt_s);
+                    float rr[3];
+                    xrot_withphase(rs, rc, rp, mm, rr);
+                    mm[0] = rr[0]; mm[1] = rr[1]; mm[2] = rr[2];
+                });
+                acc = 0.f; accg = 0.f;
+                t_old = tp;
+                cur_rf++;
+            }
+            if ((mask_ev & EV_ECHO) && scan + 1 == A.n_scans) { // kernels.cu:202-215
+                const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
+                each_scale([&](uint32_t kk, uint32_t k_acc, float *mm, const float gs, float) {
+                    dephase_relax(mm, MULTI ? fmaf(gs, accg, acc) : acc, tT1[ts], tT2[ts], dt_s);
+                    if (stage) *g.stage(A, cur_te, kk) = make_uint4(__float_as_uint(mm[0]), __float_as_uint(mm[1]), __float_as_uint(mm[2]), ts);
+                    // (the scale is part of the key: lanes of a warp that run this loop at different iterations may arrive here together)
+                    if (A.sums_fx) echo_sums_add(g.bsum, (k_acc * A.n_te + cur_te) * L.n_sub + ts, mm);
+                });
+                acc = 0.f; accg = 0.f;
+                t_old = tp;
+                cur_te++;
+            }
+            ev++;
+        } else if (seg == SEG_RUN0) { // the plain steps before a run of gradient samples are done: now the run itself
+            seg = SEG_RUN1;
+            flags |= WF_GRUN;
+            grad_first = cnt_grad;
+            rem = (int)run_len;
+            t_stop += run_len;
+            break;
+        } else if (seg == SEG_RUN1) {
+            flags &= ~WF_GRUN;
+            cnt_grad = grad_first + run_len;
+            ev += run_len;
+        } else {
+            if (seg == SEG_TAIL) { // end of TR (kernels.cu:226-231)
+                // RE-SYNCHRONISATION of multi-TR runs.  Every permeability rejection costs a walker one round, so the lanes of a warp reach their
+                // events at different rounds and — over the ~1100 TRs of a bSSFP run — drift apart completely: the event code below would run once
+                // per lane instead of once per warp.  TR number i therefore ends no earlier than round (i + 1) x A.tr_period, where the period
+                // (engine.cu) is what a walker without rejections needs for a TR plus a slack of 2 + timepoints / 64 rounds: walkers that lose
+                // fewer rounds than the slack per TR — nearly all, except behind walls at small FoV scales — stay on the common schedule, and a
+                // walker that fell behind catches up by the slack of every TR.  Deterministic per walker (absolute round numbers).
+                if (scan + 1 < A.n_scans && r_next < (scan + 1u) * A.tr_period) break; // called again at the next sync round (rem stays 0); also before a re-binning pause
+                const float dt_s = (float)((double)((n_tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
+                each_scale([&](uint32_t, uint32_t, float *mm, const float gs, float) { dephase_relax(mm, MULTI ? fmaf(gs, accg, acc) : acc, tT1[ts], tT2[ts], dt_s); });
+                scan++;
+                if (scan >= A.scan_end) { finished = true; break; }
+            }
+            { // start of a TR: phase cycling + first RF (kernels.cu:110-126)
+                each_scale([&](uint32_t, uint32_t, float *mm, float, const float lin_pc) {
+                    float ph = (float)((double)(A.rf_ph0 + (float)scan * lin_pc) + (double)(scan * (scan + 1u)) / 2.0 * (double)A.quad_pc);
+                    // the reference wraps by repeated subtraction (kernels.cu:112-113: hundreds of iterations late in a bSSFP run): whole turns in closed form first
+                    if (ph > 720.f) ph = (float)((double)ph - 360.0 * floor(((double)ph - 360.0) / 360.0));
+                    if (ph < -360.f) ph = (float)((double)ph + 360.0 * floor(-(double)ph / 360.0));
+                    while (ph > 360.0) ph = (float)(ph - 360.0);
+                    while (ph < 0) ph = (float)(ph + 360.0);
+                    float rr[3];
+                    xrot_withphase(A.s, A.c, ph, mm, rr);
+                    mm[0] = rr[0]; mm[1] = rr[1]; mm[2] = rr[2];
+                });
+                t_stop = 0; t_old = 0; ev = 0;
+                cur_rf = 1; cur_te = 0; cnt_deph = 0; cnt_grad = 0;
+                acc = 0.f; accg = 0.f;
+                if (STATS) flags |= WF_FRESH;
+            }
+        }
+        // ---- next segment: the steps up to and including the next entry's timepoint, or the plain steps before a run of
+        //      gradient-only samples at consecutive timepoints (a PGSE lobe: one sample per step), or the rest of the TR ----
+        const uint32_t ev_time = ev < L.n_tl ? (uint32_t)tl_time[ev] : n_tp;
+        uint32_t stop;
+        if (ev >= L.n_tl || ev_time >= n_tp) { stop = n_tp; seg = SEG_TAIL; }
+        else if (GRUNS && tl_run[ev] >= 2u) { stop = ev_time; seg = SEG_RUN0; run_len = min(tl_run[ev], n_tp - ev_time); }
+        else { stop = ev_time + 1u; seg = SEG_EVENT; }
+        rem = (int)(stop - t_stop);
+        t_stop = stop;
+        if (rem > 0) break;
+    }
+    if (finished) { // this launch's scans are complete (or the walker was abandoned)
+        flags |= WF_DONE;
+        rem = 0;
+        if (!MULTI && A.scan_end < A.n_scans) { // pause at a TR boundary: the round index is the whole RNG state (MULTI runs are never paused, engine.cu)
+            A.state_a[g.st_idx(A)] = make_uint4(p0, p1, p2, r_next);
+            A.state_b[g.st_idx(A)] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), ts | ((lost ? 1u : 0u) << 8));
+            A.state_vox[g.st_idx(A)] = ((p0 >> SC.fb) * A.ny + (p1 >> SC.fb)) * A.nz + (p2 >> SC.fb);
+        } else if (stage) {
+            // echoes that never fired (beyond the TR, or after the walker was abandoned) read 0, like the reference's zero-initialised
+            // outputs (monte_carlo.cu:256,259-260); the final position is the last committed one (kernels.cu:220-221)
+            const uint4 pos = make_uint4(__float_as_uint((float)((double)p0 * SC.unit_m[0])), __float_as_uint((float)((double)p1 * SC.unit_m[1])),
+                                         __float_as_uint((float)((double)p2 * SC.unit_m[2])), lost ? 1u : 0u);
+            const uint32_t k0 = MULTI ? 0u : g.k, k1 = MULTI ? A.n_multi : g.k + 1u;
+            for (uint32_t kk = k0; kk < k1; kk++) {
+                for (uint32_t e = cur_te; e < A.n_te; e++) *g.stage(A, e, kk) = make_uint4(0u, 0u, 0u, 0u);
+                if (!RECORD) *g.stage(A, A.n_te, kk) = pos;
+            }
+        }
+    } else {
+        if (!MULTI) { es[ES_M0 * nthr] = __float_as_uint(m[0]); es[ES_M1 * nthr] = __float_as_uint(m[1]); es[ES_M2 * nthr] = __float_as_uint(m[2]); }
+        es[ES_SCAN * nthr] = scan; es[ES_EV * nthr] = ev; es[ES_SEG * nthr] = seg; es[ES_TSTOP * nthr] = t_stop; es[ES_TOLD * nthr] = t_old;
+        es[ES_RF * nthr] = cur_rf; es[ES_TE * nthr] = cur_te; es[ES_DEPH * nthr] = cnt_deph; es[ES_GFIRST * nthr] = grad_first; es[ES_RUNLEN * nthr] = run_len;
+    }
+    AdvOutMulti o;
+    o.acc = acc; o.rem = rem; o.cnt_grad = cnt_grad; o.flags = flags; o.accg = accg;
+    return o;
+}
+
 // GRUNS: the sequence holds runs of gradient samples (taken inside the round); sequences without them get a kernel without that code.
 // SHARED: block = 32 spins x A.group scales sharing the spins' normals through shared memory; else block = kBlock spins of one scale.
-template <bool STATS, bool RECORD, int VOX, bool GRUNS, bool SHARED>
-__global__ void __launch_bounds__(SHARED ? SWK_FAST_SHARED_MAXT : kBlock, SHARED ? SWK_FAST_SHARED_MINB : SWK_FAST_MIN_BLOCKS)
+// MULTI (PRIVATE geometry, one "scale" per launch): one walker per spin for ALL A.n_multi gradient / phase-cycling scales (see advance_walker).
+template <bool STATS, bool RECORD, int VOX, bool GRUNS, bool SHARED, bool MULTI = false>
+__global__ void __launch_bounds__(SHARED ? SWK_FAST_SHARED_MAXT : kBlock, SHARED ? SWK_FAST_SHARED_MINB : (MULTI ? SWK_FAST_MULTI_MINB : SWK_FAST_MIN_BLOCKS))
 walk_fast_kernel(const __grid_constant__ WalkArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -422,7 +612,7 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
 
     // ---- shared memory: [sequence tables] [block sums, int64] [scale constants of this block's scales] [event state] [normals, SHARED];
     //      which (spin, scale): see Geo ----
-    const Geo<SHARED> g(A, smem);
+    const Geo<SHARED, MULTI> g(A, smem);
     const uint32_t nthr = g.nthr;
     const uint8_t *B = g.B;
     if (A.blob_in_smem) {
@@ -431,13 +621,15 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
         uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
         for (uint32_t i = threadIdx.x; i < nw; i += nthr) dst[i] = __ldg(src + i);
     }
+    static_assert(!(MULTI && (SHARED || RECORD)), "MULTI: PRIVATE geometry, no trajectory recording");
     const uint32_t n_grp = SHARED ? A.group : 1u; // scales walked by this block
+    const uint32_t n_acc = MULTI ? A.n_multi : n_grp; // scales it accumulates ensemble sums for
     const uint32_t n_bsum = g.n_bsum;             // sum entries per scale
     long long *bsum = g.bsum;
     uint32_t *es = g.es;   // field f of this thread: es[f * nthr]
     float4 *nbuf = g.nbuf; // [2][kBatch][32], SHARED only
     const uint32_t k_first = g.k_first, kc = g.k, j = g.j, jl = g.jl, spin_no = g.spin_no;
-    for (uint32_t i = threadIdx.x; i < n_bsum * n_grp; i += nthr) bsum[i] = 0;
+    for (uint32_t i = threadIdx.x; i < n_bsum * n_acc; i += nthr) bsum[i] = 0;
     {
         const uint32_t wps = A.scale_stride / 4u; // words per scale record
         const uint32_t *src = reinterpret_cast<const uint32_t *>(A.scale_tab) + (size_t)k_first * wps;
@@ -482,7 +674,13 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
                 lost = lost_before = (sb.w & 0x100u) != 0u; // abandoned in an earlier launch (already counted there)
             }
         }
-        es[ES_M0 * nthr] = __float_as_uint(m[0]); es[ES_M1 * nthr] = __float_as_uint(m[1]); es[ES_M2 * nthr] = __float_as_uint(m[2]);
+        if (MULTI) { // every scale starts from the same magnetisation
+            if (valid)
+                for (uint32_t kk = 0; kk < A.n_multi; kk++)
+                    A.mstate[(size_t)kk * A.n_local + j] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), 0u);
+        } else {
+            es[ES_M0 * nthr] = __float_as_uint(m[0]); es[ES_M1 * nthr] = __float_as_uint(m[1]); es[ES_M2 * nthr] = __float_as_uint(m[2]);
+        }
         es[ES_SCAN * nthr] = A.scan_first; es[ES_SEG * nthr] = SEG_START;
         es[ES_EV * nthr] = 0u; es[ES_TSTOP * nthr] = 0u; es[ES_TOLD * nthr] = 0u; es[ES_RF * nthr] = 1u; es[ES_TE * nthr] = 0u;
         es[ES_DEPH * nthr] = 0u; es[ES_GFIRST * nthr] = 0u; es[ES_RUNLEN * nthr] = 0u;
@@ -524,6 +722,7 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
 
     // ---- registers of the round loop ----
     float acc = 0.f;      // phase accrued since the last event (degrees)
+    float accg = 0.f;     // MULTI: its gradient part, for UNSCALED gradients (phase of scale k = acc + gscale_k accg)
     int rem = 0;          // accepted steps still to take in the current segment
     uint32_t itr = 0;     // consecutive rejections (kernels.cu:155)
     uint32_t cnt_grad = 0;
@@ -591,9 +790,13 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
             rem--;
             if (STATS) { st_field += chg; ind3_cur = ind3; fresh = false; st_steps++; }
             if (GRUNS && grun) { // gradient sample of this timepoint, at the NEW position (kernels.cu:181-187); FP32 here, FP64 in the event path
-                const float gs = SC.gscale;
-                const float gx = __fmul_rn(gtx[cnt_grad], gs), gy = __fmul_rn(gty[cnt_grad], gs), gz = __fmul_rn(gtz[cnt_grad], gs);
-                acc += gx * ((float)p0 * SC.umk[0]) + gy * ((float)p1 * SC.umk[1]) + gz * ((float)p2 * SC.umk[2]);
+                if (MULTI) {
+                    accg += gtx[cnt_grad] * ((float)p0 * SC.umk[0]) + gty[cnt_grad] * ((float)p1 * SC.umk[1]) + gtz[cnt_grad] * ((float)p2 * SC.umk[2]);
+                } else {
+                    const float gs = SC.gscale;
+                    const float gx = __fmul_rn(gtx[cnt_grad], gs), gy = __fmul_rn(gty[cnt_grad], gs), gz = __fmul_rn(gtz[cnt_grad], gs);
+                    acc += gx * ((float)p0 * SC.umk[0]) + gy * ((float)p1 * SC.umk[1]) + gz * ((float)p2 * SC.umk[2]);
+                }
                 cnt_grad++;
             }
             if (RECORD && X1) { // kernels.cu:218-221 (diagnostic mode)
@@ -605,11 +808,18 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
 
     // ======================================= events =======================================
     auto advance = [&](const uint32_t r_next) { // (see advance_walker)
-        const AdvOut o = advance_walker<STATS, RECORD, VOX, GRUNS, SHARED>(&A, p0, p1, p2, wcur, acc, cnt_grad,
-                                                                  (lost ? WF_LOST : 0u) | (grun ? WF_GRUN : 0u) | (fresh ? WF_FRESH : 0u), r_next);
-        acc = o.acc; rem = o.rem; cnt_grad = o.cnt_grad;
-        done = (o.flags & WF_DONE) != 0u; grun = (o.flags & WF_GRUN) != 0u;
-        if (STATS) fresh = (o.flags & WF_FRESH) != 0u;
+        const uint32_t fl = (lost ? WF_LOST : 0u) | (grun ? WF_GRUN : 0u) | (fresh ? WF_FRESH : 0u);
+        if constexpr (MULTI) {
+            const AdvOutMulti o = advance_walker_multi<STATS, VOX, GRUNS>(&A, p0, p1, p2, wcur, acc, accg, cnt_grad, fl, r_next);
+            acc = o.acc; rem = o.rem; cnt_grad = o.cnt_grad; accg = o.accg;
+            done = (o.flags & WF_DONE) != 0u; grun = (o.flags & WF_GRUN) != 0u;
+            if (STATS) fresh = (o.flags & WF_FRESH) != 0u;
+        } else {
+            const AdvOut o = advance_walker<STATS, RECORD, VOX, GRUNS, SHARED>(&A, p0, p1, p2, wcur, acc, cnt_grad, fl, r_next);
+            acc = o.acc; rem = o.rem; cnt_grad = o.cnt_grad;
+            done = (o.flags & WF_DONE) != 0u; grun = (o.flags & WF_GRUN) != 0u;
+            if (STATS) fresh = (o.flags & WF_FRESH) != 0u;
+        }
     };
 
     if (!done) advance(r_first); // start of the first TR of this launch
@@ -660,15 +870,16 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
     // ---- flush block sums and counters ----
     __syncthreads();
     if (A.sums_fx) {
-        for (uint32_t i = threadIdx.x; i < n_bsum * n_grp; i += nthr) {
-            const uint32_t kk = k_first + i / n_bsum;
+        for (uint32_t i = threadIdx.x; i < n_bsum * n_acc; i += nthr) {
+            const uint32_t kk = (MULTI ? 0u : k_first) + i / n_bsum;
             const long long v = bsum[i];
-            if (v != 0 && kk < A.k_hi) atomicAdd(A.sums_fx + (size_t)kk * n_bsum + (i % n_bsum), (unsigned long long)v);
+            if (v != 0 && kk < (MULTI ? A.n_multi : A.k_hi)) atomicAdd(A.sums_fx + (size_t)kk * n_bsum + (i % n_bsum), (unsigned long long)v);
         }
     }
     if (A.counters) {
         if (STATS) {
             unsigned long long c0 = st_steps, c1 = st_mask, c2 = st_field, c3 = st_rej;
+            if (MULTI) { c0 *= A.n_multi; c1 *= A.n_multi; c2 *= A.n_multi; c3 *= A.n_multi; } // the statistics of the n_multi identical walks this one stands for
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 c0 += __shfl_xor_sync(0xffffffffu, c0, o);
@@ -683,7 +894,7 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
                 atomicAdd(A.counters + 3, c3);
             }
         }
-        const unsigned lost_w = __popc(__ballot_sync(0xffffffffu, lost && !lost_before)); // spins abandoned in THIS launch
+        const unsigned lost_w = __popc(__ballot_sync(0xffffffffu, lost && !lost_before)) * (MULTI ? A.n_multi : 1u); // spins abandoned in THIS launch
         if (lane == 0 && lost_w) atomicAdd(A.counters + 4, (unsigned long long)lost_w);
     }
 }

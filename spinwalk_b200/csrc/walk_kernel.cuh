@@ -90,6 +90,10 @@ struct WalkArgs {
     uint32_t group, n_groups; // SHARED variant: scales per block (block = 32 x group threads), groups of this launch per spin chunk
     int32_t  perm_draws;     // some 0 < P_XY < 1: permeability uniforms are needed
     uint32_t tr_period;      // FAST mode, multi-TR runs: nominal rounds per TR (walk_fast.cuh: re-synchronisation at TR boundaries)
+    // FAST mode, ONE WALK FOR ALL SCALES (walk_fast.cuh MULTI): when the scales act on the gradients or on the phase cycling, every scale of a spin
+    // walks the same path (the reference re-seeds seed+spin per scale, kernels.cu:77-88); one walker per spin then carries n_multi magnetisations
+    uint32_t n_multi;        // 0: off, else the number of scales
+    uint4   *mstate;         // [n_multi][n_local] by thread slot: (Mx, My, Mz, -) of every scale between two sequence events
     // outputs (any may be nullptr)
     // Per-spin results go to STAGING ROWS, one per (scale, local spin): n_te echo slots (Mx, My, Mz, tissue) and one slot for the final
     // position, 16 bytes each — a thread's scattered result write is whole aligned 16/32-byte pieces instead of three partial-sector

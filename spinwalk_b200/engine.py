@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib as L
-from ._lib import MODE_COMPAT, MODE_FAST, OUT_ALL, OUT_M1, OUT_T, OUT_XYZ1, RUN_NO_PACK, RUN_NO_REBIN, RUN_NO_SORT, RUN_STATS, RUN_ZSLAB, RUN_NO_ZSLAB, RUN_NO_SHARE, SCALE_FOV, SCALE_GRADIENT, SCALE_PHASE_CYCLING  # noqa: F401
+from ._lib import MODE_COMPAT, MODE_FAST, OUT_ALL, OUT_M1, OUT_T, OUT_XYZ1, RUN_NO_PACK, RUN_NO_REBIN, RUN_NO_SORT, RUN_STATS, RUN_ZSLAB, RUN_NO_ZSLAB, RUN_NO_SHARE, RUN_NO_ONEWALK, SCALE_FOV, SCALE_GRADIENT, SCALE_PHASE_CYCLING  # noqa: F401
 
 
 class EngineError(RuntimeError):

@@ -405,14 +405,55 @@ def test_shared_and_private_streams_agree(sw):
             e.set_phantom(mask, fm, fov)
             e.set_sequence(cfg)
             e.set_spins(xyz0)
-            st0 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS)
+            st0 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_NO_ONEWALK)
             shared = e.download() + (e.sums(),)
-            st1 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_NO_SHARE)
+            st1 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_NO_SHARE | sw.RUN_NO_ONEWALK)
             private = e.download() + (e.sums(),)
         for a, b in zip(shared, private):
             assert np.array_equal(a, b), name
         for key in ("steps", "mask_gathers", "field_gathers", "rejects", "lost"):
             assert st0[key] == st1[key], (name, key)
+
+
+@pytest.mark.parametrize("name", ["pgse", "ssfp", "events_edge", "stuck_gradient"])
+def test_one_walk_for_all_scales_equals_one_walk_per_scale(sw, name, monkeypatch):
+    """WHAT_TO_SCALE = 1 (gradients) or 2 (phase cycling): every scale of a spin walks the same path — the reference re-seeds seed+spin per
+    scale (kernels.cu:77-88) and the FoV is not scaled — so by default ONE walker per spin carries the magnetisation of every scale
+    (walk_fast.cuh MULTI).  Against one walker per (spin, scale) (SWK_RUN_NO_ONEWALK): final positions, tissues at echo and the lost count are
+    bit-identical, the counters are the per-scale counters times the number of scales, and the magnetisations agree to FP32 round-off (the
+    gradient phase is scaled after the sum instead of term by term).  Gradient runs (PGSE lobes), single gradient samples, dummy scans with phase
+    cycling, several echoes, abandoned spins; one launch and the sliced host run."""
+    if name == "stuck_gradient":  # abandoned spins (kernels.cu:155-159) under gradient scaling: echoes written before the loss are kept, later ones read 0
+        case, mask, fm, fov, xyz0 = cases.stuck()
+        case.scales, case.scale_type = [0.0, 1.0, 3.0], cases.po.SCALE_GRADIENT
+        case.gradient_tp, case.gradX_mTm, case.gradY_mTm, case.gradZ_mTm = [10, 11, 12, 100], [20.0, 20.0, 20.0, -5.0], [0.0, 1.0, 0.0, 0.0], [3.0, 0.0, 0.0, 0.0]
+    else:
+        case, mask, fm, fov, xyz0 = cases.ALL[name]()
+    cfg = cases.to_simconfig(case)
+    K = case.n_scales
+    with sw.Engine(0) as e:
+        e.set_phantom(mask, fm, fov)
+        e.set_sequence(cfg)
+        e.set_spins(xyz0)
+        st1 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS)
+        one = e.download() + (e.sums(),)
+        stk = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_NO_ONEWALK)
+        per = e.download() + (e.sums(),)
+        monkeypatch.setenv("SWK_SLICES", "3")
+        host = e.run(xyz0, mode=sw.MODE_FAST)
+    (m1, x1, t, s1), (m1k, x1k, tk, sk) = one, per
+    assert np.array_equal(x1, x1k) and np.array_equal(t, tk), name
+    for k in range(1, K):
+        assert np.array_equal(x1[k], x1[0]) and np.array_equal(t[k], t[0])
+    np.testing.assert_allclose(m1, m1k, rtol=0, atol=3e-5, err_msg=name)
+    assert np.abs(m1k).max() > 0.1 and (K < 2 or np.abs(m1k[0] - m1k[-1]).max() > 1e-3)  # the scales do differ
+    np.testing.assert_allclose(s1[..., :3], sk[..., :3], rtol=0, atol=3e-5 * case.n_spins)
+    assert np.array_equal(s1[..., 3], sk[..., 3])
+    for key in ("steps", "mask_gathers", "field_gathers", "rejects", "lost"):
+        assert st1[key] == stk[key], (name, key)
+    if name == "stuck_gradient":
+        assert st1["lost"] > 0
+    assert np.array_equal(host["M1"], m1) and np.array_equal(host["XYZ1"], x1) and np.array_equal(host["T"], t) and np.array_equal(host["sums"], s1)
 
 
 def test_scales_do_not_depend_on_their_neighbours(sw):
