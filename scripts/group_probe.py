@@ -1,5 +1,5 @@
 """Kernel time of the C2 workload per group of 10 consecutive FoV scales and as a whole, for kernel-variant choices given on the command line.
-Diagnostic, not the bench.  python scripts/group_probe.py SPINS WORKLOAD name[:ENV=VAL,...] ...   (flags via env: SWK_NO_SHARE, SWK_GROUP, SWK_SHARE_SIGMA)"""
+Diagnostic, not the bench.  python scripts/group_probe.py SPINS WORKLOAD name[:ENV=VAL,...] ...   (flags via env: SWK_NO_SHARE, SWK_GROUP, SWK_SHARE_SIGMA; PROBE_MODE=compat, PROBE_FLAGS)"""
 import os
 import sys
 
@@ -18,6 +18,7 @@ eng.set_sequence(cfg)
 eng.set_spins(bench.make_positions(S, eng.fov, cfg.seed))
 sc = list(cfg.scales)
 fl = int(os.environ.get("PROBE_FLAGS", "0"))
+MODE = sw.MODE_COMPAT if os.environ.get("PROBE_MODE") == "compat" else sw.MODE_FAST
 for v in variants:
     name, _, envs = v.partition(":")
     keys = []
@@ -28,10 +29,10 @@ for v in variants:
     row = []
     for g in range(0, len(sc), 10):
         part = sc[g:g + 10]
-        eng.run_device(scales=part, mode=sw.MODE_FAST, flags=fl)
-        row.append(min(eng.run_device(scales=part, mode=sw.MODE_FAST, flags=fl)["kernel_ms"] for _ in range(2)))
-    eng.run_device(mode=sw.MODE_FAST, flags=fl)
-    ms = min(eng.run_device(mode=sw.MODE_FAST, flags=fl)["kernel_ms"] for _ in range(2))
+        eng.run_device(scales=part, mode=MODE, flags=fl)
+        row.append(min(eng.run_device(scales=part, mode=MODE, flags=fl)["kernel_ms"] for _ in range(2)))
+    eng.run_device(mode=MODE, flags=fl)
+    ms = min(eng.run_device(mode=MODE, flags=fl)["kernel_ms"] for _ in range(2))
     print(f"{name:14s} groups of 10 scales: " + " ".join(f"{x:7.2f}" for x in row) + f" ms  sum {sum(row):7.2f}  all at once {ms:7.2f} ms = {S * len(sc) * cfg.n_timepoints / ms / 1e6:7.2f} Gsteps/s", flush=True)
     for k in keys:
         os.environ.pop(k, None)

@@ -62,7 +62,7 @@ struct swk_engine {
     bool packed_valid = false;
     bool packed_brick = false; // layout of `packed`: 2 x 2 x 4 bricks instead of row-major
     DevBuf slab;            // SWK_RUN_ZSLAB: packed words of one z plane, [nx][ny]
-    bool slab_valid = false;
+    bool slab_valid = false, raw_slab_valid = false;
     bool last_used_slab = false; // the last run walked the z slab: swk_probe_gather probes that table
     int z_invariant = -1;   // -1 not checked yet, 0 / 1: mask and field map do not depend on z
     uint64_t dims[3] = {0, 0, 0};
@@ -81,6 +81,7 @@ struct swk_engine {
     // spins
     DevBuf xyz0, m0, order, inv_order; // inv_order: spin -> thread slot (unpack_rows_kernel)
     DevBuf state_a, state_b, state_vox;                     // re-binning pauses of long runs: per (scale, spin) walker state
+    DevBuf raw_slab;                                        // COMPAT mode, z-invariant phantom: (substrate id, FP32 field bits) of one z plane
     DevBuf mstate;                                          // one walk for all scales (walk_fast.cuh MULTI): magnetisation per (scale, thread slot)
     DevBuf sort_keys_in, sort_keys_out, sort_ids, sort_tmp; // kept between runs: re-sorting after every swk_set_spins must not malloc
     bool order_valid = false;
@@ -219,6 +220,12 @@ __global__ void zinv_check_kernel(const uint8_t *mask, const float *field, size_
 __global__ void pack_slab_kernel(const uint8_t *mask, const float *field, size_t nxy, uint32_t nz, uint32_t *out)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nxy; i += (size_t)gridDim.x * blockDim.x) out[i] = pack_word(field[i * nz], mask[i * nz]);
+}
+// ... and, for SWK_MODE_COMPAT, the UNROUNDED pair (substrate id, FP32 field bits) of the z = 0 plane: one 8-byte gather per voxel change
+__global__ void raw_slab_kernel(const uint8_t *mask, const float *field, size_t nxy, uint32_t nz, uint2 *out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nxy; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = make_uint2(mask[i * nz], __float_as_uint(field[i * nz]));
 }
 
 // With slice_len != 0 the slice number of the spin (id / slice_len) leads the key, so that the sorted order is slice-major
@@ -434,7 +441,7 @@ void swk_destroy(swk_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     for (DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->mstate, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
+                      &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->mstate, &e->raw_slab, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
         release(*b);
     if (e->evA) cudaEventDestroy(e->evA);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -475,7 +482,7 @@ int swk_set_phantom(swk_engine *e, const uint8_t *mask, const float *fieldmap_T,
     release(e->packed);
     e->packed_valid = false;
     release(e->slab);
-    e->slab_valid = false;
+    e->slab_valid = false; e->raw_slab_valid = false;
     e->z_invariant = -1;
     int rc;
     if ((rc = ensure(e, e->mask, V)) != SWK_OK) return rc;
@@ -841,8 +848,11 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     const bool want_packed = mode == SWK_MODE_FAST && e->fieldmap.p && e->mask_substrates <= 16 && !(flags & SWK_RUN_NO_PACK);
     // a phantom that does not depend on z (every cylinder phantom of `spinwalk phantom -c`) is walked on its [nx][ny] slab: the same
     // words, hence the same results bit for bit, from a table nz times smaller (L1/L2 resident).  Checked once per phantom on the device.
-    bool use_slab = false;
-    if (want_packed && !(flags & SWK_RUN_NO_ZSLAB) && getenv("SWK_NO_ZSLAB") == nullptr && e->dims[2] > 1) {
+    // COMPAT mode walks the same plane through raw (substrate id, FP32 field) pairs: the very values of the full arrays, so T / XYZ1 / M1 stay
+    // bit-identical to the reference's (tests/test_engine_gpu.py), from an L2-resident table and with one gather instead of two.
+    bool use_slab = false, use_raw_slab = false;
+    const bool compat_slab = mode == SWK_MODE_COMPAT && e->fieldmap.p != nullptr;
+    if ((want_packed || compat_slab) && !(flags & SWK_RUN_NO_ZSLAB) && getenv("SWK_NO_ZSLAB") == nullptr && e->dims[2] > 1) {
         const size_t V = (size_t)(e->dims[0] * e->dims[1] * e->dims[2]), nxy = (size_t)(e->dims[0] * e->dims[1]);
         if (e->z_invariant < 0) {
             unsigned int differs = 0;
@@ -855,7 +865,17 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             e->z_invariant = differs ? 0 : 1;
             extra_launches++;
         }
-        if (e->z_invariant == 1) {
+        if (e->z_invariant == 1 && compat_slab) {
+            if (!e->raw_slab_valid) {
+                if ((rc = ensure(e, e->raw_slab, nxy * sizeof(uint2))) != SWK_OK) return rc;
+                raw_slab_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), static_cast<const float *>(e->fieldmap.p), nxy,
+                                                                       (uint32_t)e->dims[2], static_cast<uint2 *>(e->raw_slab.p));
+                CK(cudaGetLastError());
+                e->raw_slab_valid = true;
+                extra_launches++;
+            }
+            use_raw_slab = true;
+        } else if (e->z_invariant == 1) {
             if (!e->slab_valid) {
                 if ((rc = ensure(e, e->slab, nxy * sizeof(uint32_t))) != SWK_OK) return rc;
                 pack_slab_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(static_cast<const uint8_t *>(e->mask.p), static_cast<const float *>(e->fieldmap.p), nxy,
@@ -890,6 +910,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     A.fieldmap = static_cast<const float *>(e->fieldmap.p);
     A.packed = want_packed ? static_cast<const uint32_t *>(use_slab ? e->slab.p : e->packed.p) : nullptr;
     A.brick = (want_packed && !use_slab && e->packed_brick) ? 1 : 0;
+    A.raw_slab = use_raw_slab ? static_cast<const uint2 *>(e->raw_slab.p) : nullptr;
     A.nx = (uint32_t)e->dims[0]; A.ny = (uint32_t)e->dims[1]; A.nz = (uint32_t)e->dims[2];
     A.V = (int64_t)(e->dims[0] * e->dims[1] * e->dims[2]);
     for (int i = 0; i < 3; i++) A.fov[i] = e->fov[i];
@@ -1413,7 +1434,7 @@ uint64_t swk_device_bytes(const swk_engine *e)
     if (!e) return 0;
     uint64_t n = 0;
     for (const DevBuf *b : {&e->mask, &e->fieldmap, &e->packed, &e->blob, &e->xyz0, &e->m0, &e->order, &e->scales, &e->M1, &e->XYZ1, &e->T, &e->sums, &e->counters,
-                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->mstate, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
+                            &e->sort_keys_in, &e->sort_keys_out, &e->sort_ids, &e->sort_tmp, &e->state_a, &e->state_b, &e->state_vox, &e->mstate, &e->raw_slab, &e->slab, &e->stage, &e->sums_fx, &e->scale_tab, &e->inv_order})
         n += b->bytes;
     return n;
 }
@@ -1570,7 +1591,7 @@ int swk_generate_phantom(swk_engine *e, const swk_phantom_spec *spec, swk_phanto
     release(e->packed);
     e->packed_valid = false;
     release(e->slab);
-    e->slab_valid = false;
+    e->slab_valid = false; e->raw_slab_valid = false;
     e->z_invariant = -1;
     if ((rc = ensure(e, e->mask, V)) != SWK_OK) return rc;
     if (calc && (rc = ensure(e, e->fieldmap, V * sizeof(float))) != SWK_OK) return rc;

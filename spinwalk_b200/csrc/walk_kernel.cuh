@@ -53,6 +53,7 @@ struct WalkArgs {
     const float   *fieldmap; // Tesla at 1 T, or nullptr
     const uint32_t *packed;  // FAST mode: packed voxel words (engine.cu pack_word), or nullptr
     int32_t  brick;          // the packed volume is stored in 2 x 2 x 4 bricks (walk_fast.cuh table_index)
+    const uint2 *raw_slab;   // COMPAT mode, phantom invariant along z: (substrate id, FP32 field bits) of one z plane [nx][ny], or nullptr
     uint32_t nx, ny, nz;
     int64_t  V;
     float    fov[3];         // metres (held as float like the reference, monte_carlo.cuh:37)
@@ -420,8 +421,16 @@ __global__ void __launch_bounds__(kBlock) walk_compat_kernel(const WalkArgs A)
                 }
                 if (fresh || ind_new != ind_cur) { // kernels.cu:150-170
                     if (STATS) st_mask++;
-                    const uint32_t ts = __ldg(A.mask + ind_new);
-                    float fv = has_field ? __ldg(A.fieldmap + ind_new) : 0.f; // issued together with the mask gather
+                    uint32_t ts;
+                    float fv;
+                    if (A.raw_slab) { // the same two values from the [nx][ny] plane of a z-invariant phantom: one 8-byte gather (engine.cu raw_slab_kernel)
+                        const uint2 w = __ldg(A.raw_slab + (ix * (int64_t)A.ny + iy));
+                        ts = w.x;
+                        fv = __uint_as_float(w.y);
+                    } else {
+                        ts = __ldg(A.mask + ind_new);
+                        fv = has_field ? __ldg(A.fieldmap + ind_new) : 0.f; // issued together with the mask gather
+                    }
                     if (ts != ts_old) {
                         if (minstd_uniform(rng_u) >= tpXY[ts_old * L.n_sub + ts]) {
                             if (STATS) st_rej++;

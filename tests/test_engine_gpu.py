@@ -354,6 +354,22 @@ def test_zslab_walks_the_same_path(sw):
         assert np.array_equal(a, b)  # (the sums too: they are accumulated in integer fixed point)
     for key in ("steps", "mask_gathers", "field_gathers", "rejects", "lost"):
         assert st0[key] == st1[key], key
+    # COMPAT mode walks the raw (substrate id, FP32 field) pairs of the same plane: the values of the full arrays, bit-identical results
+    for name in ("se", "ssfp", "events_edge"):
+        case, mask, fm, fov, xyz0 = cases.ALL[name]()
+        cfg = cases.to_simconfig(case)
+        with sw.Engine(0) as e:
+            e.set_phantom(mask, fm, fov)
+            e.set_sequence(cfg)
+            e.set_spins(xyz0)
+            st0 = e.run_device(mode=sw.MODE_COMPAT, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_NO_ZSLAB)
+            base = e.download() + (e.sums(),)
+            st1 = e.run_device(mode=sw.MODE_COMPAT, flags=sw.OUT_ALL | sw.RUN_STATS)
+            slab = e.download() + (e.sums(),)
+        for a, b in zip(base, slab):
+            assert np.array_equal(a, b), name
+        for key in ("steps", "mask_gathers", "field_gathers", "rejects", "lost"):
+            assert st0[key] == st1[key], (name, key)
     # not invariant along z: the full table, whatever the flag
     case, mask, fm, fov, xyz0 = cases.multi_echo(n_spins=400)
     cfg = cases.to_simconfig(case)
