@@ -467,7 +467,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "compat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (full_table, compat, scale_groups, non_invariant, north_star)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (full_table, compat, scale_groups, non_invariant, gradient_scales, other_configs, north_star)")
     args = ap.parse_args()
     protect_stdout()
     if args.workload == "ph-mesh":
@@ -575,7 +575,8 @@ def main():
     # ---- sub-records (every N): the same engine on the configurations VERDICT r1 asked for, each a bounded, separately timed run
     if args.workload == "c2" and mode == sw.MODE_FAST and not args.no_extras and not args.spins and not args.scales:
         for name, fn in (("full_table", W.extra_full_table), ("compat", W.extra_compat), ("scale_groups", W.extra_scale_groups),
-                         ("non_invariant", W.extra_non_invariant), ("north_star", W.extra_north_star)):
+                         ("non_invariant", W.extra_non_invariant), ("gradient_scales", W.extra_gradient_scales), ("other_configs", W.extra_other_configs),
+                         ("north_star", W.extra_north_star)):
             try:
                 line[name] = fn(peak, peak_src, args)
             except Exception as ex:  # an extra must never cost the headline line
@@ -798,7 +799,7 @@ class Walk:
         T = self.timed(H, sw.MODE_COMPAT, sw.OUT_ALL, 2, 1)
         rec = {"value": H["steps_per_pass"] * self.world * 2 / (T["dev_ms"] * 1e-3), "unit": "spin-steps/s", "ms_per_step": T["dev_ms"] / 2, "steps": 2, "warmup": 1,
                "dtype": "f32+f64", "config": {"workload": desc.replace("1e7 spins", "2e6 of the 1e7 spins") + "; SWK_MODE_COMPAT (bit-exact T / XYZ1 vs the reference's cu_sim, "
-                                              "tests/test_engine_gpu.py); mask byte + FP32 field from the full arrays", "spins_per_gpu": H["S"]}}
+                                              "tests/test_engine_gpu.py); z-invariant phantom: raw (substrate id, FP32 field) pairs of one z plane, the values of the full arrays", "spins_per_gpu": H["S"]}}
         self.close(H)
         return rec
 
@@ -838,6 +839,46 @@ class Walk:
         rec["roofline"]["gather"] = self.gather_roofline(H, sw.MODE_FAST)
         self.close(H)
         return rec
+
+    def extra_gradient_scales(self, peak, peak_src, args):
+        """BASELINE.json configs[2] (C3): PGSE on the 400^3 permeable-sphere phantom, 1e7 spins x 51 GRADIENT scales (b = 100..5000, 0).  Gradient scales do
+        not change the walk and the reference replays one random stream per spin for every scale (kernels.cu:77-88): one walker per spin carries the
+        magnetisation of all 51 scales (walk_fast.cuh MULTI; SWK_RUN_NO_ONEWALK walks every scale separately — the `per_scale_walks` leg, 1e6 spins)"""
+        sw = self.sw
+        out = {}
+        for name in ("c3", "c3r"):
+            cfg_kw, ph, desc = workload(name, None, None)
+            H = self.setup(name, cfg_kw, ph)
+            T = self.timed(H, sw.MODE_FAST, sw.OUT_ALL, 2, 1)
+            rec = {"value": H["steps_per_pass"] * self.world * 2 / (T["dev_ms"] * 1e-3), "unit": "spin-steps/s", "ms_per_step": T["dev_ms"] / 2, "kernel_ms_per_step": T["ker_ms"] / 2,
+                   "steps": 2, "warmup": 1, "config": {"workload": desc, "spins_per_gpu": H["S"], "n_scales": H["K"], "timepoints": H["cfg"].n_timepoints,
+                                                       "note": "spin-steps = spins x scales x timepoints, the work the reference does; one walk per spin serves all scales"}}
+            S1 = 1_000_000
+            H["eng"].set_spins(H["xyz0_pin"].numpy()[:S1], None, H["spin_first"])
+            H1 = dict(H, S=S1, steps_per_pass=S1 * H["K"] * H["cfg"].n_timepoints)
+            T1 = self.timed(H1, sw.MODE_FAST, sw.OUT_ALL | sw.RUN_NO_ONEWALK, 1, 1)
+            rec["per_scale_walks"] = {"value": H1["steps_per_pass"] * self.world / (T1["dev_ms"] * 1e-3), "unit": "spin-steps/s", "ms_per_step": T1["dev_ms"], "spins_per_gpu": S1,
+                                      "note": "SWK_RUN_NO_ONEWALK: one walker per (spin, scale), as round 1 ran it"}
+            self.close(H)
+            self.torch.cuda.empty_cache()
+            out[name] = rec
+        return out
+
+    def extra_other_configs(self, peak, peak_src, args):
+        """the remaining BASELINE.json configurations, so that one line carries all five: C1 (GRE BOLD, 100^3, 1e5 spins x 50 FoV scales) at full size and
+        C4 (bSSFP, 1101 TRs x 200 steps, one scale) on 2e6 of its 1e7 spins"""
+        sw = self.sw
+        out = {}
+        for name, spins, steps in (("c1", None, 5), ("c4", 2_000_000, 1)):
+            cfg_kw, ph, desc = workload(name, spins, None)
+            H = self.setup(name, cfg_kw, ph)
+            T = self.timed(H, sw.MODE_FAST, sw.OUT_ALL, steps, 1)
+            out[name] = {"value": H["steps_per_pass"] * self.world * steps / (T["dev_ms"] * 1e-3), "unit": "spin-steps/s", "ms_per_step": T["dev_ms"] / steps, "steps": steps, "warmup": 1,
+                         "config": {"workload": desc if spins is None else desc.replace("1e7 spins", f"{spins:.0e} of the 1e7 spins".replace("e+0", "e")), "spins_per_gpu": H["S"],
+                                    "n_scales": H["K"], "timepoints": H["cfg"].n_timepoints, "scans": H["eng"].n_dummy_scan + 1}}
+            self.close(H)
+            self.torch.cuda.empty_cache()
+        return out
 
     def extra_north_star(self, peak, peak_src, args):
         """BASELINE.json configs[4] / north_star: 1000^3 BOLD phantom, 1.25e8 spins per GPU (1e9 over 8), 50 FoV scales, ensemble sums only, NCCL all-reduce"""

@@ -1024,7 +1024,11 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         if (fixed_private > smem_cap) return fail(e, SWK_ERR_INVALID, "too many echoes x substrates for the in-kernel ensemble sums");
         // ONE WALK FOR ALL SCALES (walk_fast.cuh MULTI): gradient and phase-cycling scales do not change the walk, and the reference replays the same
         // random stream for every scale of a spin (kernels.cu:77-88), so one walker per spin carries the magnetisation of every scale (A.mstate).
-        const size_t fixed_multi = ((bsum_bytes * K + 15) & ~size_t(15)) + stride + (size_t)ES_FIELDS * 4 * kBlock;
+        size_t fixed_multi = ((bsum_bytes * K + 15) & ~size_t(15)) + stride + (size_t)ES_FIELDS * 4 * kBlock;
+        if (gruns && fixed_multi + (size_t)e->L.n_grad * sizeof(float4) + e->L.bytes <= smem_cap) { // pre-multiplied gradient samples in shared memory
+            fixed_multi += (size_t)e->L.n_grad * sizeof(float4);
+            A.g4_smem = 1;
+        }
         onewalk = scale_type != SWK_SCALE_FOV && K > 1 && !record && !(flags & SWK_RUN_NO_ONEWALK) && getenv("SWK_NO_ONEWALK") == nullptr &&
                   fixed_multi <= smem_cap;
         if (onewalk) {
@@ -1348,9 +1352,10 @@ int swk_run(swk_engine *e, const float *XYZ0, const float *M0, uint32_t spin_fir
     if ((rc = swk_set_spins(e, XYZ0, M0, spin_first, n_local)) != SWK_OK) return rc;
     tr.mark("set_spins (H2D)");
     const int flags = (M1 ? SWK_OUT_M1 : 0) | (XYZ1 ? SWK_OUT_XYZ1 : 0) | (T ? SWK_OUT_T : 0) | (stats ? SWK_RUN_STATS : 0);
-    // Large runs are cut into <= 8 slices of >= 2^21 spins so that the device-to-host copy of slice i overlaps the walk of slice
-    // i+1 (measured on C2: 4 slices cost 0.5 % each in kernel time and leave 1/4 of the 0.24 s download exposed).
-    uint32_t n_slices = (M1 || XYZ1 || T) ? std::min<uint32_t>(8u, std::max<uint32_t>(1u, n_local >> 21)) : 1u;
+    // Large runs are cut into <= 16 slices of >= 2^19 spins so that the device-to-host copy of slice i overlaps the walk of slice
+    // i+1; the download of the LAST slice is what stays exposed (measured on C2, 1e7 spins, 12.5 GB out: 1462 / 1412 / 1387 ms per pass
+    // end to end with 4 / 8 / 16 slices against 1329 ms of kernels, profiles/README.md).
+    uint32_t n_slices = (M1 || XYZ1 || T) ? std::min<uint32_t>(16u, std::max<uint32_t>(1u, n_local >> 19)) : 1u;
     // Long runs (bSSFP: 220 200 steps per walker) stay in one piece: their download is < 1 % of the walk (a walker's 25 output bytes
     // cost what ~160 steps cost), and only an unsliced run pauses for re-binning (run_impl) — C4: 1.56e11 sliced vs 2.15e11 spin-steps/s.
     if (e->has_sequence && !e->P.record_trajectory && (uint64_t)e->P.n_timepoints * (uint64_t)(e->P.n_dummy_scan + 1) >= 16000u) n_slices = 1;

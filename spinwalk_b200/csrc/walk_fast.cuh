@@ -448,6 +448,11 @@ __device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, con
     const float *tT1 = blob_ptr<float>(B, L.T1s), *tT2 = blob_ptr<float>(B, L.T2s);
     const uint32_t ts = (VOX == VOX_PACKED || VOX == VOX_SLAB) ? (wcur & 15u) : wcur; // the substrate does not change during events
     const bool lost = (flags & WF_LOST) != 0u;
+    // relaxation over dt: the same factors for every scale (dephase_relax, kernels.cu:45-52)
+    const float T1 = tT1[ts], T2 = tT2[ts];
+    const bool relax = T1 >= 0 && T2 >= 0;
+    float e1 = 0.f, e2 = 0.f;
+    auto relax_factors = [&](const float dt_s) { if (relax) { e1 = expf(-dt_s / T1); e2 = expf(-dt_s / T2); } };
 
     float m[3] = {0.f, 0.f, 0.f};
     if (!MULTI) { m[0] = __uint_as_float(es[ES_M0 * nthr]); m[1] = __uint_as_float(es[ES_M1 * nthr]); m[2] = __uint_as_float(es[ES_M2 * nthr]); }
@@ -494,8 +499,9 @@ __device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, con
             if (mask_ev & EV_RF) { // kernels.cu:190-199
                 const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
                 const float rs = blob_ptr<float>(B, L.rf_s)[cur_rf], rc = blob_ptr<float>(B, L.rf_c)[cur_rf], rp = blob_ptr<float>(B, L.rf_ph)[cur_rf];
+                relax_factors(dt_s);
                 each_scale([&](uint32_t, uint32_t, float *mm, const float gs, float) {
-                    dephase_relax(mm, MULTI ? fmaf(gs, accg, acc) : acc, tT1[ts], tT2[ts], dt_s);
+                    dephase_relax_pre(mm, fmaf(gs, accg, acc), relax, e1, e2);
                     float rr[3];
                     xrot_withphase(rs, rc, rp, mm, rr);
                     mm[0] = rr[0]; mm[1] = rr[1]; mm[2] = rr[2];
@@ -506,8 +512,9 @@ __device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, con
             }
             if ((mask_ev & EV_ECHO) && scan + 1 == A.n_scans) { // kernels.cu:202-215
                 const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
+                relax_factors(dt_s);
                 each_scale([&](uint32_t kk, uint32_t k_acc, float *mm, const float gs, float) {
-                    dephase_relax(mm, MULTI ? fmaf(gs, accg, acc) : acc, tT1[ts], tT2[ts], dt_s);
+                    dephase_relax_pre(mm, fmaf(gs, accg, acc), relax, e1, e2);
                     if (stage) *g.stage(A, cur_te, kk) = make_uint4(__float_as_uint(mm[0]), __float_as_uint(mm[1]), __float_as_uint(mm[2]), ts);
                     // (the scale is part of the key: lanes of a warp that run this loop at different iterations may arrive here together)
                     if (A.sums_fx) echo_sums_add(g.bsum, (k_acc * A.n_te + cur_te) * L.n_sub + ts, mm);
@@ -538,7 +545,8 @@ __device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, con
                 // walker that fell behind catches up by the slack of every TR.  Deterministic per walker (absolute round numbers).
                 if (scan + 1 < A.n_scans && r_next < (scan + 1u) * A.tr_period) break; // called again at the next sync round (rem stays 0); also before a re-binning pause
                 const float dt_s = (float)((double)((n_tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
-                each_scale([&](uint32_t, uint32_t, float *mm, const float gs, float) { dephase_relax(mm, MULTI ? fmaf(gs, accg, acc) : acc, tT1[ts], tT2[ts], dt_s); });
+                relax_factors(dt_s);
+                each_scale([&](uint32_t, uint32_t, float *mm, const float gs, float) { dephase_relax_pre(mm, fmaf(gs, accg, acc), relax, e1, e2); });
                 scan++;
                 if (scan >= A.scan_end) { finished = true; break; }
             }
@@ -637,6 +645,12 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
             reinterpret_cast<uint32_t *>(g.sct)[i] = (k_first + i / wps) < A.k_hi ? __ldg(src + i) : 0u;
     }
     __syncthreads();
+    if (MULTI && GRUNS && A.g4_smem) { // gradient samples, pre-multiplied with the degrees of phase per (mT/m x fixed-point unit) of each axis: one LDS.128 per sample
+        const ScaleConst &S0 = g.sc(A);
+        const float *tx = blob_ptr<float>(B, L.gx), *ty = blob_ptr<float>(B, L.gy), *tz = blob_ptr<float>(B, L.gz);
+        for (uint32_t i = threadIdx.x; i < L.n_grad; i += nthr) nbuf[i] = make_float4(tx[i] * S0.umk[0], ty[i] * S0.umk[1], tz[i] * S0.umk[2], 0.f);
+        __syncthreads();
+    }
 
     const bool valid = g.valid;
     const ScaleConst &SC = g.sc(A);
@@ -791,7 +805,10 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
             if (STATS) { st_field += chg; ind3_cur = ind3; fresh = false; st_steps++; }
             if (GRUNS && grun) { // gradient sample of this timepoint, at the NEW position (kernels.cu:181-187); FP32 here, FP64 in the event path
                 if (MULTI) {
-                    accg += gtx[cnt_grad] * ((float)p0 * SC.umk[0]) + gty[cnt_grad] * ((float)p1 * SC.umk[1]) + gtz[cnt_grad] * ((float)p2 * SC.umk[2]);
+                    if (A.g4_smem) {
+                        const float4 g4 = nbuf[cnt_grad];
+                        accg += g4.x * (float)p0 + g4.y * (float)p1 + g4.z * (float)p2;
+                    } else accg += gtx[cnt_grad] * ((float)p0 * SC.umk[0]) + gty[cnt_grad] * ((float)p1 * SC.umk[1]) + gtz[cnt_grad] * ((float)p2 * SC.umk[2]);
                 } else {
                     const float gs = SC.gscale;
                     const float gx = __fmul_rn(gtx[cnt_grad], gs), gy = __fmul_rn(gty[cnt_grad], gs), gz = __fmul_rn(gtz[cnt_grad], gs);

@@ -95,6 +95,7 @@ struct WalkArgs {
     // walks the same path (the reference re-seeds seed+spin per scale, kernels.cu:77-88); one walker per spin then carries n_multi magnetisations
     uint32_t n_multi;        // 0: off, else the number of scales
     uint4   *mstate;         // [n_multi][n_local] by thread slot: (Mx, My, Mz, -) of every scale between two sequence events
+    int32_t  g4_smem;        // MULTI kernels with gradient runs: the block keeps (gx, gy, gz) x degrees-per-unit of every gradient sample in shared memory
     // outputs (any may be nullptr)
     // Per-spin results go to STAGING ROWS, one per (scale, local spin): n_te echo slots (Mx, My, Mz, tissue) and one slot for the final
     // position, 16 bytes each — a thread's scattered result write is whole aligned 16/32-byte pieces instead of three partial-sector
@@ -152,6 +153,20 @@ __device__ __forceinline__ void dephase_relax(float *m, float acc_phase_deg, flo
     zrot(sp, cp, m, r);
     if (T1 >= 0 && T2 >= 0) {
         float e1 = expf(-dt_s / T1), e2 = expf(-dt_s / T2);
+        r[0] = r[0] * e2;
+        r[1] = r[1] * e2;
+        r[2] = 1. + e1 * (r[2] - 1.);
+    }
+    m[0] = r[0]; m[1] = r[1]; m[2] = r[2];
+}
+
+// the same with the relaxation factors e1 = exp(-dt / T1), e2 = exp(-dt / T2) computed by the caller (they do not depend on the scale: MULTI kernels)
+__device__ __forceinline__ void dephase_relax_pre(float *m, float acc_phase_deg, bool relax, float e1, float e2)
+{
+    float r[3];
+    float sp = sinf(acc_phase_deg * kDeg2Rad), cp = cosf(acc_phase_deg * kDeg2Rad);
+    zrot(sp, cp, m, r);
+    if (relax) {
         r[0] = r[0] * e2;
         r[1] = r[1] * e2;
         r[2] = 1. + e1 * (r[2] - 1.);
