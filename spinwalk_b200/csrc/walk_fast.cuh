@@ -30,7 +30,7 @@
 #define SWK_FAST_MIN_BLOCKS 5 // PRIVATE variant: 48 registers, 40 warps per SM
 #endif
 #ifndef SWK_FAST_MULTI_MINB
-#define SWK_FAST_MULTI_MINB 4  // MULTI variant (one walker per spin for all gradient / phase-cycling scales): 64 registers, 32 warps per SM
+#define SWK_FAST_MULTI_MINB 3  // MULTI variant (one walker per spin for all gradient / phase-cycling scales): 80 registers, 24 warps per SM (C3, blocks per SM 2 / 3 / 4 / 5 / 6: 4.6 / 5.6 / 5.2 / 5.1 / 3.6e12)
 #endif
 #ifndef SWK_FAST_SHARED_MAXT
 #define SWK_FAST_SHARED_MAXT 320 // SHARED variant: at most 10 scales (warps) per block
@@ -160,7 +160,10 @@ __device__ __forceinline__ uint32_t ldg_voxel(const uint32_t *p)
 enum { VOX_MASK = 0, VOX_SPLIT = 1, VOX_PACKED = 2, VOX_SLAB = 3 };
 
 constexpr int kUnroll = SWK_FAST_UNROLL;
-constexpr uint32_t kSync = 8;   // a walker runs its sequence events at rounds that are multiples of kSync (see the file header)
+#ifndef SWK_KSYNC
+#define SWK_KSYNC 8
+#endif
+constexpr uint32_t kSync = SWK_KSYNC;   // a walker runs its sequence events at rounds that are multiples of kSync (see the file header)
 constexpr uint32_t kBatch = 16; // SHARED variant: rounds of normals generated per barrier (32 spins x 16 rounds = 256 Philox blocks)
 
 // Per-scale constants, computed once per run on the host in double precision (engine.cu scale_constants) and staged in shared
