@@ -262,23 +262,30 @@ def test_rebinned_long_run_equals_uninterrupted_run(sw, oracle, monkeypatch, sca
     """Long runs (many TRs) are paused at TR boundaries to re-sort the spins by their current voxel (engine.cu run_impl).  The
     pause stores position, magnetisation, substrate and the RNG block counter and the walk resumes from exactly that state, so
     the outputs must equal the uninterrupted run bit for bit — with one order per scale (FoV scaling) and with a shared order
-    (phase-cycling scaling).  SWK_REBIN_SCANS=3 forces a pause every 3 TRs on a test-sized run."""
+    (phase-cycling scaling, one walker per (spin, scale): SWK_RUN_NO_ONEWALK — the default for such scales, one walk for all of them, is
+    never paused).  SWK_REBIN_SCANS=3 forces a pause every 3 TRs on a test-sized run."""
     case, mask, fm, fov, xyz0 = cases.ssfp(n_spins=1500)
     if scale_type_name == "FOV":
         case.scale_type, case.scales = oracle.SCALE_FOV, [0.7, 1.0, 1.9]
     cfg = cases.to_simconfig(case)
+    per_scale = sw.RUN_NO_ONEWALK
     with sw.Engine(0) as e:
         e.set_phantom(mask, fm, fov)
         e.set_sequence(cfg)
         e.set_spins(xyz0)
         assert e.n_dummy_scan >= 20
-        st0 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_NO_REBIN | sw.RUN_STATS)
+        st0 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_NO_REBIN | sw.RUN_STATS | per_scale)
         ref = e.download() + (e.sums(),)
         monkeypatch.setenv("SWK_REBIN_SCANS", "3")
-        st1 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS)
+        st1 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | per_scale)
         got = e.download() + (e.sums(),)
+        if scale_type_name == "PHASE_CYCLING":  # one walk for all scales: one launch whatever the re-binning knob says, same walk
+            st3 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS)
+            one = e.download()
+            assert st3["n_launches"] <= 3 and np.array_equal(one[1], ref[1]) and np.array_equal(one[2], ref[2])
+            np.testing.assert_allclose(one[0], ref[0], rtol=0, atol=3e-5)
         monkeypatch.delenv("SWK_REBIN_SCANS")
-        st2 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL)  # back to one launch: the start order is still valid
+        st2 = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | per_scale)  # back to one launch: the start order is still valid
         again = e.download()
     assert st1["n_launches"] > st0["n_launches"] + 5
     for a, b, c in zip(ref[:3], got[:3], again):
