@@ -16,7 +16,7 @@ ncu --metrics $M --clock-control none -k regex:"walk_compat" --csv --log-file $O
 python scripts/make_traffic.py c2:fast=$O/r02_traffic_c2.csv:10000000 c2:fast:full=$O/r02_traffic_c2_full.csv:10000000 c5:fast=$O/r02_traffic_c5.csv:25000000 c5:fast:full=$O/r02_traffic_c5_full.csv:25000000 c3:fast:full=$O/r02_traffic_c3.csv:2000000 c2:compat=$O/r02_traffic_c2_compat.csv:2000000 > $O/r02_traffic_json.log 2>&1
 cp profiles/traffic.json $O/traffic.json
 tail -3 $O/r02_traffic_json.log
-if [ "$1" != "quick" ]; then
+if [ "$1" = "full" ]; then
 ncu --set full --import-source on --clock-control none -k regex:walk_fast -o $O/r02_full_c2 -f python bench.py --spins 2000000 $B > $O/r02_full_c2.log 2>&1
 ncu -i $O/r02_full_c2.ncu-rep --page details --csv > $O/r02_full_c2_details.csv 2>/dev/null
 ncu -i $O/r02_full_c2.ncu-rep --page source --csv --print-source sass --launch-skip 3 --launch-count 1 > $O/r02_full_c2_source_shared.csv 2>/dev/null

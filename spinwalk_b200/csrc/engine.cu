@@ -970,6 +970,7 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
     std::vector<Part> parts;
     walk_fn kern_private = nullptr; // FAST: the variant of legs resumed after a re-binning pause (walkers resume at their own rounds)
     bool onewalk = false;           // FAST: one walker per spin for all (gradient / phase-cycling) scales
+    size_t multi_chunk = 0;         // ... walked in chunks of this many thread slots (== S unless the run has no per-spin outputs)
     size_t smem_private = 0;
     const size_t bsum_bytes = A.sums_fx ? E * ns * 4 * sizeof(long long) : 0;
     if (mode == SWK_MODE_COMPAT) {
@@ -1032,9 +1033,16 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
         onewalk = scale_type != SWK_SCALE_FOV && K > 1 && !record && !(flags & SWK_RUN_NO_ONEWALK) && getenv("SWK_NO_ONEWALK") == nullptr &&
                   fixed_multi <= smem_cap;
         if (onewalk) {
-            if ((rc = ensure(e, e->mstate, K * S * sizeof(uint4))) != SWK_OK) return rc;
+            // magnetisations of every scale between two events: 16 bytes per (scale, walker).  Runs with per-spin outputs hold 16 (E + 1) bytes of staging
+            // rows per (scale, walker) anyway; runs without them (ensemble sums only: 1e8 and more spins per GPU) walk chunks of slots one after the other
+            // so that this buffer stays bounded
+            multi_chunk = (!want_stage && n_slices == 1) ? (size_t)std::min<uint64_t>(S, std::max<uint64_t>(kBlock, ((256ull << 20) / K) / kBlock * kBlock)) : S;
+            if (const char *ev = getenv("SWK_MULTI_CHUNK")) multi_chunk = std::min<size_t>(S, (size_t)std::max(1, atoi(ev)) * kBlock); // test hook
+            if ((rc = ensure(e, e->mstate, K * multi_chunk * sizeof(uint4))) != SWK_OK) return rc;
             A.n_multi = (uint32_t)K;
             A.mstate = static_cast<uint4 *>(e->mstate.p);
+            A.m_first = 0;
+            A.m_rows = (uint32_t)multi_chunk;
         }
         // SHARED variant (walk_fast.cuh): 32 spins x G scales per block share the spins' normals: ~45 instead of ~90 instructions per attempt
         // where the launch is issue bound.  Where every attempt fetches a voxel far from the last one (step sigma above ~1 voxel: the small FoV
@@ -1226,6 +1234,13 @@ static int run_impl(swk_engine *e, const float *scales, uint32_t n_scales, int s
             }
             CK(unpack(0, S, e->stream));
             CK(cudaStreamSynchronize(e->stream)); // order2 is freed on return
+        } else if (onewalk && multi_chunk < S) { // ensemble sums only: chunk after chunk through the same magnetisation buffer
+            for (size_t c0 = 0; c0 < S; c0 += multi_chunk) {
+                A.j_first = (uint32_t)c0;
+                A.j_end = (uint32_t)std::min(S, c0 + multi_chunk);
+                A.m_first = A.j_first;
+                if ((rc = launch_walk(e->stream, false, false)) != SWK_OK) return rc;
+            }
         } else {
             if ((rc = launch_walk(e->stream, true, false)) != SWK_OK) return rc;
             CK(unpack(0, S, e->stream));

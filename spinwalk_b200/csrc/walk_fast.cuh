@@ -463,7 +463,7 @@ __device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, con
     auto each_scale = [&](auto &&fn) {
         if (MULTI) {
             for (uint32_t kk = 0; kk < A.n_multi; kk++) {
-                uint4 *slot = A.mstate + (size_t)kk * A.n_local + g.j;
+                uint4 *slot = A.mstate + (size_t)kk * A.m_rows + (g.j - A.m_first);
                 const uint4 v = *slot;
                 float mm[3] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z)};
                 const ScaleConst *sk = reinterpret_cast<const ScaleConst *>(A.scale_tab + (size_t)kk * A.scale_stride);
@@ -694,7 +694,7 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
         if (MULTI) { // every scale starts from the same magnetisation
             if (valid)
                 for (uint32_t kk = 0; kk < A.n_multi; kk++)
-                    A.mstate[(size_t)kk * A.n_local + j] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), 0u);
+                    A.mstate[(size_t)kk * A.m_rows + (j - A.m_first)] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), 0u);
         } else {
             es[ES_M0 * nthr] = __float_as_uint(m[0]); es[ES_M1 * nthr] = __float_as_uint(m[1]); es[ES_M2 * nthr] = __float_as_uint(m[2]);
         }

@@ -94,7 +94,8 @@ struct WalkArgs {
     // FAST mode, ONE WALK FOR ALL SCALES (walk_fast.cuh MULTI): when the scales act on the gradients or on the phase cycling, every scale of a spin
     // walks the same path (the reference re-seeds seed+spin per scale, kernels.cu:77-88); one walker per spin then carries n_multi magnetisations
     uint32_t n_multi;        // 0: off, else the number of scales
-    uint4   *mstate;         // [n_multi][n_local] by thread slot: (Mx, My, Mz, -) of every scale between two sequence events
+    uint4   *mstate;         // [n_multi][m_rows], row = thread slot - m_first: (Mx, My, Mz, -) of every scale between two sequence events
+    uint32_t m_first, m_rows; // (runs without per-spin outputs walk chunks of m_rows slots one after the other: bounded memory, engine.cu)
     int32_t  g4_smem;        // MULTI kernels with gradient runs: the block keeps (gx, gy, gz) x degrees-per-unit of every gradient sample in shared memory
     // outputs (any may be nullptr)
     // Per-spin results go to STAGING ROWS, one per (scale, local spin): n_te echo slots (Mx, My, Mz, tissue) and one slot for the final

@@ -462,6 +462,11 @@ def test_one_walk_for_all_scales_equals_one_walk_per_scale(sw, name, monkeypatch
         one = e.download() + (e.sums(),)
         stk = e.run_device(mode=sw.MODE_FAST, flags=sw.OUT_ALL | sw.RUN_STATS | sw.RUN_NO_ONEWALK)
         per = e.download() + (e.sums(),)
+        # ensemble sums only (no per-spin output): the walk goes chunk after chunk through a bounded magnetisation buffer (SWK_MULTI_CHUNK: 256 slots)
+        monkeypatch.setenv("SWK_MULTI_CHUNK", "1")
+        e.run_device(mode=sw.MODE_FAST, flags=0)
+        assert np.array_equal(e.sums(), one[3]), name  # (fixed-point sums: exact whatever the chunking)
+        monkeypatch.delenv("SWK_MULTI_CHUNK")
         monkeypatch.setenv("SWK_SLICES", "3")
         host = e.run(xyz0, mode=sw.MODE_FAST)
     (m1, x1, t, s1), (m1k, x1k, tk, sk) = one, per
