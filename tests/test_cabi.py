@@ -34,6 +34,25 @@ def test_library_exports_every_header_symbol(engine_lib):
     assert engine_lib.swk_version() == 1
 
 
+def test_enum_values_match_the_header():
+    """modes, scale types, output and run flags, error codes: the ctypes mirror holds the values a C program sees in the header."""
+    import subprocess
+    import tempfile
+
+    from spinwalk_b200 import _lib
+
+    names = ["SWK_OK", "SWK_ERR_INVALID", "SWK_ERR_CUDA", "SWK_ERR_MEMORY", "SWK_ERR_STATE", "SWK_ERR_SUBSTRATE", "SWK_SCALE_FOV", "SWK_SCALE_GRADIENT",
+             "SWK_SCALE_PHASE_CYCLING", "SWK_MODE_COMPAT", "SWK_MODE_FAST", "SWK_OUT_M1", "SWK_OUT_XYZ1", "SWK_OUT_T", "SWK_OUT_ALL", "SWK_RUN_STATS", "SWK_RUN_NO_SORT",
+             "SWK_RUN_NO_PACK", "SWK_RUN_NO_REBIN", "SWK_RUN_ZSLAB", "SWK_RUN_NO_ZSLAB", "SWK_RUN_NO_SHARE", "SWK_RUN_NO_ONEWALK"]
+    prog = '#include <stdio.h>\n#include "spinwalk_engine.h"\nint main(){' + "".join(f'printf("%d\\n", (int){n});' for n in names) + "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "e.c"), "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "e.c"), "-o", os.path.join(d, "e")], check=True)
+        out = [int(v) for v in subprocess.run([os.path.join(d, "e")], capture_output=True, text=True, check=True).stdout.split()]
+    mirror = [getattr(_lib, n[4:] if not n.startswith("SWK_OK") and not n.startswith("SWK_ERR") else n) for n in names]
+    assert out == mirror, dict(zip(names, zip(out, mirror)))
+
+
 def test_struct_sizes_match_the_header(engine_lib):
     """ctypes mirrors of swk_params / swk_tables / swk_stats have the C layout (checked via a tiny C program)."""
     import subprocess
