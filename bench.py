@@ -109,6 +109,17 @@ def full_phantom(ph, mask2, fm2):
     return mask, fm
 
 
+def workload_config(desc, ph, S_per_gpu, K, n_tp, scans, world, slab):
+    """`config` of the JSON line: what the workload IS — the same dict, key for key, from the GPU arm and from `--impl reference`
+    (everything that describes how an arm runs it goes to `details`)."""
+    return {"workload": desc, "spins_per_gpu": int(S_per_gpu), "n_scales": int(K), "timepoints": int(n_tp), "scans": int(scans),
+            "spin_steps_per_pass": int(S_per_gpu) * int(K) * int(n_tp) * int(scans) * int(world),
+            "l2": ("per-spin outputs (12.5 GB > L2) rewritten every pass; the voxel table of this z-invariant phantom is its [nx][ny] slab (L1/L2 resident) — "
+                   "`full_table` is the same workload on the full [nx][ny][nz] table (larger than L2)") if slab else
+                  (f"inputs larger than L2 (voxel table {4 * ph['n'] ** 3 / 1e9:.2f} GB vs 126 MB)" if ph["n"] >= 400 else "phantom fits in L2; outputs rewritten every pass"),
+            "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums"}
+
+
 def make_positions(S, fov, seed, first=0):
     """uniform in [1%,99%] of the FoV (distribution of monte_carlo.cu:142-151); numpy stream, chunked by global id."""
     rng = np.random.default_rng([seed, first])
@@ -485,6 +496,7 @@ def main():
         if rank != 0:
             return
         mask2, fm2, fov = reference_phantom(ph)
+        ref_case = oracle_case(cfg_kw, ph["n"], fov)
         vals, samples = [], None
         tgt = 12.0
         for i in range(args.warmup + args.steps):
@@ -499,8 +511,10 @@ def main():
         emit({"impl": "reference", "metric": "spin-steps/s", "value": v, "unit": "spin-steps/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / max(1, args.steps),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
-                          "data": "synthetic", "config": {"workload": desc, "note": "each step = bounded sample of the workload on host cores; the phantom is "
-                                                          "the recipe's own (oracle restatement of `spinwalk phantom`, bit-identical to what the GPU arm generates)"},
+                          "data": "synthetic", "config": workload_config(desc, ph, cfg_kw["n_spins"], len(cfg_kw["scales"]), ref_case.n_timepoints, ref_case.n_dummy + 1,
+                                                                         args.gpus, ph["kind"] != "spheres" and os.environ.get("SWK_NO_ZSLAB") is None),
+                          "details": {"note": "each step = bounded sample of the workload on host cores (rank 0 only); the phantom is the recipe's own (oracle restatement of "
+                                              "`spinwalk phantom`, bit-identical to what the GPU arm generates)"},
                           "cpu_baseline": samples, "gpu_launches": 0,
                           "e2e": {"value": v, "unit": "spin-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
@@ -547,16 +561,10 @@ def main():
     line = {"metric": "spin-steps/s", "value": value, "unit": "spin-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": T["dev_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if mode == sw.MODE_FAST else "f32+f64", "data": "synthetic",
-            "config": {"workload": desc, "spins_per_gpu": S_per_gpu, "n_scales": K, "timepoints": H["cfg"].n_timepoints,
-                       "scans": H["eng"].n_dummy_scan + 1, "spin_steps_per_pass": H["steps_per_pass"] * world,
-                       "rng": "philox4x32-10 (one block per two rounds, shared by all FoV scales of a spin) + Box-Muller (SWK_MODE_FAST)" if mode == sw.MODE_FAST
-                              else "minstd_rand + erfcinvf (SWK_MODE_COMPAT, reference arithmetic)",
-                       "voxel_table": H["table"],
-                       "l2": "per-spin outputs (12.5 GB > L2) rewritten every pass; the voxel table of this z-invariant phantom is its [nx][ny] slab (L1/L2 resident) — "
-                             "`full_table` below is the same workload on the full [nx][ny][nz] table (larger than L2)" if H["slab"] else
-                             f"inputs larger than L2 (voxel table {4 * ph['n'] ** 3 / 1e9:.2f} GB vs 126 MB)" if ph["n"] >= 400 else "phantom fits in L2; outputs rewritten every pass",
-                       "phantom": H["phantom_note"],
-                       "parallelism": f"spins sharded over {world} GPU(s), phantom replicated, NCCL all-reduce of per-echo sums"},
+            "config": workload_config(desc, ph, S_per_gpu, K, H["cfg"].n_timepoints, H["eng"].n_dummy_scan + 1, world, H["slab"]),
+            "details": {"rng": "philox4x32-10 (one block per two rounds, shared by all FoV scales of a spin) + Box-Muller (SWK_MODE_FAST)" if mode == sw.MODE_FAST
+                               else "minstd_rand + erfcinvf (SWK_MODE_COMPAT, reference arithmetic)",
+                        "voxel_table": H["table"], "phantom": H["phantom_note"]},
             "clocks": clocks, "wall_ms_per_step": T["wall_ms"] / args.steps, "gpu_launches": args.steps * T["st"]["n_launches"],
             "e2e": e2e, "roofline": roofline, "lost_spins": counts["lost"]}
 
