@@ -438,7 +438,7 @@ def test_shared_and_private_streams_agree(sw):
             assert st0[key] == st1[key], (name, key)
 
 
-@pytest.mark.parametrize("name", ["pgse", "ssfp", "events_edge", "stuck_gradient"])
+@pytest.mark.parametrize("name", ["pgse", "ssfp", "events_edge", "stuck_gradient", "long_lobes"])
 def test_one_walk_for_all_scales_equals_one_walk_per_scale(sw, name, monkeypatch):
     """WHAT_TO_SCALE = 1 (gradients) or 2 (phase cycling): every scale of a spin walks the same path — the reference re-seeds seed+spin per
     scale (kernels.cu:77-88) and the FoV is not scaled — so by default ONE walker per spin carries the magnetisation of every scale
@@ -450,6 +450,11 @@ def test_one_walk_for_all_scales_equals_one_walk_per_scale(sw, name, monkeypatch
         case, mask, fm, fov, xyz0 = cases.stuck()
         case.scales, case.scale_type = [0.0, 1.0, 3.0], cases.po.SCALE_GRADIENT
         case.gradient_tp, case.gradX_mTm, case.gradY_mTm, case.gradZ_mTm = [10, 11, 12, 100], [20.0, 20.0, 20.0, -5.0], [0.0, 1.0, 0.0, 0.0], [3.0, 0.0, 0.0, 0.0]
+    elif name == "long_lobes":  # 6400 gradient samples: neither the sequence tables nor the pre-multiplied gradient table fit shared memory (the global-memory paths)
+        case, mask, fm, fov, xyz0 = cases.pgse(n_spins=160)
+        lobe = list(range(50, 3250)) + list(range(3400, 6600))
+        case.TR_us, case.TE_tp, case.RF_tp = 6700 * 50, [6650], [0, 3300]
+        case.gradient_tp, case.gradX_mTm, case.gradY_mTm, case.gradZ_mTm = lobe, [0.6] * len(lobe), [0.3] * len(lobe), [0.0] * len(lobe)
     else:
         case, mask, fm, fov, xyz0 = cases.ALL[name]()
     cfg = cases.to_simconfig(case)
