@@ -459,12 +459,15 @@ __device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, con
 
     float m[3] = {0.f, 0.f, 0.f};
     if (!MULTI) { m[0] = __uint_as_float(es[ES_M0 * nthr]); m[1] = __uint_as_float(es[ES_M1 * nthr]); m[2] = __uint_as_float(es[ES_M2 * nthr]); }
-    // fn(scale, magnetisation, gradient scale, linear phase cycling) for this walker's scale — MULTI: for every scale of the run in turn
-    auto each_scale = [&](auto &&fn) {
+    // fn(scale, magnetisation, gradient scale, linear phase cycling) for this walker's scale — MULTI: for every scale of the run in turn.
+    // `from_first`: every scale still holds the magnetisation the walker started with, which only slot 0 carries (start of the first TR).
+    auto each_scale = [&](const bool from_first, auto &&fn) {
         if (MULTI) {
+            uint4 *slot0 = A.mstate + (g.j - A.m_first);
+            const uint4 v0 = from_first ? *slot0 : make_uint4(0u, 0u, 0u, 0u);
             for (uint32_t kk = 0; kk < A.n_multi; kk++) {
-                uint4 *slot = A.mstate + (size_t)kk * A.m_rows + (g.j - A.m_first);
-                const uint4 v = *slot;
+                uint4 *slot = slot0 + (size_t)kk * A.m_rows;
+                const uint4 v = from_first ? v0 : *slot;
                 float mm[3] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z)};
                 const ScaleConst *sk = reinterpret_cast<const ScaleConst *>(A.scale_tab + (size_t)kk * A.scale_stride);
                 fn(kk, kk, mm, __ldg(&sk->gscale), __ldg(&sk->lin_pc));
@@ -503,7 +506,7 @@ __device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, con
                 const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
                 const float rs = blob_ptr<float>(B, L.rf_s)[cur_rf], rc = blob_ptr<float>(B, L.rf_c)[cur_rf], rp = blob_ptr<float>(B, L.rf_ph)[cur_rf];
                 relax_factors(dt_s);
-                each_scale([&](uint32_t, uint32_t, float *mm, const float gs, float) {
+                each_scale(false, [&](uint32_t, uint32_t, float *mm, const float gs, float) {
                     dephase_relax_pre(mm, fmaf(gs, accg, acc), relax, e1, e2);
                     float rr[3];
                     xrot_withphase(rs, rc, rp, mm, rr);
@@ -516,7 +519,7 @@ __device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, con
             if ((mask_ev & EV_ECHO) && scan + 1 == A.n_scans) { // kernels.cu:202-215
                 const float dt_s = (float)((double)((tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
                 relax_factors(dt_s);
-                each_scale([&](uint32_t kk, uint32_t k_acc, float *mm, const float gs, float) {
+                each_scale(false, [&](uint32_t kk, uint32_t k_acc, float *mm, const float gs, float) {
                     dephase_relax_pre(mm, fmaf(gs, accg, acc), relax, e1, e2);
                     if (stage) *g.stage(A, cur_te, kk) = make_uint4(__float_as_uint(mm[0]), __float_as_uint(mm[1]), __float_as_uint(mm[2]), ts);
                     // (the scale is part of the key: lanes of a warp that run this loop at different iterations may arrive here together)
@@ -548,13 +551,15 @@ __device__ __noinline__ AdvOutMulti advance_walker_multi(const WalkArgs *pA, con
                 // walker that fell behind catches up by the slack of every TR.  Deterministic per walker (absolute round numbers).
                 if (scan + 1 < A.n_scans && r_next < (scan + 1u) * A.tr_period) break; // called again at the next sync round (rem stays 0); also before a re-binning pause
                 const float dt_s = (float)((double)((n_tp - t_old) * (uint32_t)A.timestep_us) * 1e-6);
-                relax_factors(dt_s);
-                each_scale([&](uint32_t, uint32_t, float *mm, const float gs, float) { dephase_relax_pre(mm, fmaf(gs, accg, acc), relax, e1, e2); });
+                if (scan + 1 < A.n_scans) { // (what the LAST scan leaves behind is read by nobody: kernels.cu:226-231 has no output after it)
+                    relax_factors(dt_s);
+                    each_scale(false, [&](uint32_t, uint32_t, float *mm, const float gs, float) { dephase_relax_pre(mm, fmaf(gs, accg, acc), relax, e1, e2); });
+                }
                 scan++;
                 if (scan >= A.scan_end) { finished = true; break; }
             }
             { // start of a TR: phase cycling + first RF (kernels.cu:110-126)
-                each_scale([&](uint32_t, uint32_t, float *mm, float, const float lin_pc) {
+                each_scale(seg == SEG_START, [&](uint32_t, uint32_t, float *mm, float, const float lin_pc) {
                     float ph = (float)((double)(A.rf_ph0 + (float)scan * lin_pc) + (double)(scan * (scan + 1u)) / 2.0 * (double)A.quad_pc);
                     // the reference wraps by repeated subtraction (kernels.cu:112-113: hundreds of iterations late in a bSSFP run): whole turns in closed form first
                     if (ph > 720.f) ph = (float)((double)ph - 360.0 * floor(((double)ph - 360.0) / 360.0));
@@ -691,10 +696,8 @@ walk_fast_kernel(const __grid_constant__ WalkArgs A)
                 lost = lost_before = (sb.w & 0x100u) != 0u; // abandoned in an earlier launch (already counted there)
             }
         }
-        if (MULTI) { // every scale starts from the same magnetisation
-            if (valid)
-                for (uint32_t kk = 0; kk < A.n_multi; kk++)
-                    A.mstate[(size_t)kk * A.m_rows + (j - A.m_first)] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), 0u);
+        if (MULTI) { // every scale starts from the same magnetisation: slot 0 carries it to the start of the first TR (advance_walker_multi, from_first)
+            if (valid) A.mstate[j - A.m_first] = make_uint4(__float_as_uint(m[0]), __float_as_uint(m[1]), __float_as_uint(m[2]), 0u);
         } else {
             es[ES_M0 * nthr] = __float_as_uint(m[0]); es[ES_M1 * nthr] = __float_as_uint(m[1]); es[ES_M2 * nthr] = __float_as_uint(m[2]);
         }
